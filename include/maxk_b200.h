@@ -1,0 +1,156 @@
+/*
+ * maxk_b200.h -- C ABI of the B200-native MaxK aggregation hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain device
+ * pointers and sizes (no torch types), launches on the caller's stream, never
+ * synchronises, never prints and returns a status (0 = ok).  All pointers are
+ * DEVICE pointers unless a parameter says "host".  Outputs are written in full
+ * by the callee (no caller-side zero fill is required).
+ *
+ * Each function cites the reference interface it replaces (paths are relative to
+ * julius-sk/spgemm-prunning).  The reference's own C ABI
+ * (cuda_kernel_wrappers.cu:36-93, declared cuda_kernel_bindings.cpp:11-35) passes
+ * dim3 by value through extern "C" and launches on the legacy stream; this ABI is
+ * the same three operations with a real C signature.
+ *
+ * Layouts
+ *   CSR adjacency : row_begin[n_rows], row_end[n_rows] int32 (for a plain CSR pass
+ *                   indptr and indptr+1), indices[E] int32 source-node ids, values[E] fp32.
+ *   CBSR features : cbsr_val[n_src, k] fp32 + cbsr_sel[n_src, k] uint8 column ids,
+ *                   row stride exactly k, columns distinct within a row
+ *                   (kernels/spmm_maxk.cu:17 vin_data / vin_selector).
+ *   warp4         : int32 quads (row, loc, len<=max_nz, 0) (kernels/generate_meta.py:30-48).
+ */
+#ifndef MAXK_B200_H
+#define MAXK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes: 0 ok, >0 a cudaError_t from the launch, <0 argument errors below. */
+#define MAXK_OK 0
+#define MAXK_ERR_BAD_K (-1)          /* k < 1 or k > dim                                   */
+#define MAXK_ERR_BAD_DIM (-2)        /* dim < 1 or dim > 256 (uint8 selector)  */
+#define MAXK_ERR_NULL (-3)           /* a required pointer is NULL                         */
+#define MAXK_ERR_WORKSPACE (-4)      /* workspace too small                                */
+#define MAXK_ERR_ALIGN (-5)          /* a pointer is not 16-byte aligned                   */
+#define MAXK_ERR_SIZE (-6)           /* negative or overflowing size                       */
+
+typedef void *maxk_stream_t; /* a cudaStream_t */
+
+/* Library identification; also lets a binding check it loaded the right .so. */
+int maxk_abi_version(void);
+const char *maxk_status_string(int status);
+
+/* top-k output order */
+#define MAXK_ORDER_VALUE_DESC 0 /* (value desc, column asc): torch.topk(sorted=True) order */
+#define MAXK_ORDER_COLUMN_ASC 1 /* column ascending: cheapest, used by the fused layer     */
+
+/*
+ * (1) MaxK row-wise top-k -> CBSR.
+ * Replaces torch.topk(x, k, dim=1) + .to(uint8) (maxk_spgemm_function.py:53-57,
+ * model_integrated_v3.py:32, spgemmfunction_v4:50-51) and the uint8 `topk` kernel behind
+ * cuda_topk_maxk / cuda_topk_maxk_float / prepare_cbsr_format_maxk
+ * (cuda_kernel_bindings.cpp:164-251, kernels/maxk_kernel.cu:23-96).
+ * Exact: the k largest of each row, NaN largest, -0 == +0, ties broken by LOWEST column.
+ *   x          [n_rows, dim] fp32
+ *   cbsr_val   [n_rows, k]   fp32   (required)
+ *   cbsr_sel   [n_rows, k]   uint8  (nullable)
+ *   idx_i32    [n_rows, k]   int32  (nullable; the dtype cuda_topk_maxk_float returns)
+ *   idx_i64    [n_rows, k]   int64  (nullable; the dtype torch.topk returns)
+ *   masked     [n_rows, dim] fp32   (nullable; x with every non-selected entry set to 0 =
+ *                                    the MaxK nonlinearity output, maxk_models_integrated.py:28-37)
+ */
+int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
+                   float *cbsr_val, uint8_t *cbsr_sel, int32_t *idx_i32, int64_t *idx_i64,
+                   float *masked, maxk_stream_t stream);
+
+/*
+ * (2) Forward row-wise-product SpGEMM: out = A_csr x scatter(CBSR)   (optionally / row_div).
+ * Replaces spmm_kernel_opt2_sparse_v3_wrapper / spmm_maxk_forward
+ * (cuda_kernel_wrappers.cu:38-56, cuda_kernel_bindings.cpp:42-104, kernels/spmm_maxk.cu:17-106).
+ *   out[r, cbsr_sel[c,l]] += values[e] * cbsr_val[c,l]  for every edge e=(r,c), l<k
+ *   out      [n_rows, dim] fp32, fully written (rows without edges become 0)
+ *   row_div  [n_rows] fp32 nullable: out[r,:] /= row_div[r] fused into the epilogue
+ *            (the reference does it in Python: maxk_spgemm_function.py:86, spgemmfunction_v4:72)
+ *   workspace: maxk_spgemm_workspace_bytes(n_rows) bytes of device scratch.
+ * Deterministic: each output row is reduced in a fixed order (no atomics).
+ */
+int maxk_spgemm_forward(const int32_t *row_begin, const int32_t *row_end,
+                        const int32_t *indices, const float *values,
+                        const float *cbsr_val, const uint8_t *cbsr_sel,
+                        float *out, int64_t n_rows, int64_t n_edges, int dim, int k,
+                        const float *row_div,
+                        void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+
+/*
+ * (3) Backward outer-product SSpMM: gs = sample_sel(A^T (g / row_div)).
+ * Replaces spmm_kernel_opt2_sparse_backward_v3_wrapper / spmm_maxk_backward
+ * (cuda_kernel_wrappers.cu:58-76, cuda_kernel_bindings.cpp:106-161,
+ *  kernels/spmm_maxk_backward.cu:15-115).
+ *   gs[c, l] += values[e] * g[r, cbsr_sel[c,l]]          for every edge e=(r,c), l<k
+ *   g        [n_rows, dim] fp32   gs [n_dst, k] fp32, fully written (zero-filled inside)
+ *   row_div  [n_rows] fp32 nullable: g[r,:] / row_div[r] fused into the row stage
+ *            (maxk_spgemm_function.py:155, spgemmfunction_v4:87)
+ * Called with the same CSR as (2) it is the exact adjoint of (2).
+ */
+int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_end,
+                        const int32_t *indices, const float *values,
+                        const float *g, const uint8_t *cbsr_sel,
+                        float *gs, int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
+                        const float *row_div,
+                        void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+
+/* Scratch needed by (2) and (3) for a CSR with n_rows rows. */
+size_t maxk_spgemm_workspace_bytes(int64_t n_rows);
+
+/*
+ * (4) warp4 partition metadata built on the GPU.
+ * Replaces the host loop of kernels/generate_meta.py:30-48 and the file round trip of
+ * load_warp4_metadata (cuda_kernel_bindings.cpp:287-317).
+ * Two phases because the quad count W must be known to allocate:
+ *   maxk_warp4_scan : seg_offsets[n_rows+1] int32 = exclusive scan of ceil(deg/max_nz);
+ *                     W = seg_offsets[n_rows] (read it back on the host).
+ *   maxk_warp4_fill : warp4[4*W] from indptr + seg_offsets.
+ *   scan_workspace  : maxk_warp4_workspace_bytes(n_rows) bytes.
+ */
+size_t maxk_warp4_workspace_bytes(int64_t n_rows);
+int maxk_warp4_scan(const int32_t *indptr, int64_t n_rows, int max_nz, int32_t *seg_offsets,
+                    void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+int maxk_warp4_fill(const int32_t *indptr, const int32_t *seg_offsets, int64_t n_rows, int max_nz,
+                    int32_t *warp4, maxk_stream_t stream);
+/*
+ * Inverse: recover per-row edge ranges from warp4 quads so that (2)/(3) can be driven by
+ * the reference's metadata alone (spmm_maxk_forward receives warp4 but no indptr,
+ * cuda_kernel_bindings.cpp:42-50).  Rows absent from warp4 get begin = end = 0.
+ * Quads must be well formed (generate_meta.py): grouped by row, contiguous locs.
+ */
+int maxk_warp4_to_rows(const int32_t *warp4, int64_t n_quads, int64_t n_rows,
+                       int32_t *row_begin, int32_t *row_end, maxk_stream_t stream);
+
+/*
+ * (5) Helpers of the operator surface.
+ * maxk_cbsr_scatter: dense[r, sel[r,l]] = vals[r,l], everything else 0.  Replaces
+ *   zeros(...).scatter_(1, sel.long(), grad_sparse) (maxk_spgemm_function.py:152,175).
+ * maxk_mask_apply  : out[r,j] = in[r,j] if j in sel[r,:] else 0.  Replaces grad * mask of
+ *   MaxK.backward (maxk_models_integrated.py:40-43) without the saved fp32 mask.
+ *   When add_vals is non-NULL, out[r, sel[r,l]] additionally += add_vals[r,l]
+ *   (the aggregation gradient that OPTMaxK.backward drops).
+ * maxk_dense_spmm  : out = A_csr x dense, fp32.  Stands in for the reference's
+ *   cusparse_spmm validation helper (cuda_kernel_bindings.cpp:253-284) without cuSPARSE.
+ */
+int maxk_cbsr_scatter(const float *vals, const uint8_t *sel, int64_t n_rows, int dim, int k,
+                      float *dense, maxk_stream_t stream);
+int maxk_mask_apply(const float *in, const uint8_t *sel, const float *add_vals,
+                    int64_t n_rows, int dim, int k, float *out, maxk_stream_t stream);
+int maxk_dense_spmm(const int32_t *indptr, const int32_t *indices, const float *values,
+                    const float *dense, int64_t n_rows, int dim, float *out, maxk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAXK_B200_H */

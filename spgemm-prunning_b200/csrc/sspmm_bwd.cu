@@ -1,0 +1,275 @@
+// sspmm_bwd.cu -- backward outer-product SSpMM (sm_100a).
+//
+// Replaces spmm_kernel_opt2_sparse_backward_v3 (reference kernels/spmm_maxk_backward.cu:15-115):
+//   gs[c, l] += val[e] * g[r, sel[c,l]]    for every edge e=(r,c), l<k
+// Design (DESIGN.md "Backward SSpMM"):
+//   * outer-product form kept: a warp stages its source row g[r,0:256] (1 KiB, coalesced,
+//     fused /row_div) in shared memory once and walks the row's edges; the gather form would
+//     re-read up to 1 KiB of g per EDGE.
+//   * the E*k scalar fp32 atomics of the reference (spmm_maxk_backward.cu:80,101) become
+//     E*k/4 16-byte vector reductions (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4):
+//     a lane owns 4 consecutive entries of one destination row, k/4 lanes cover an edge and
+//     128/k edges are processed per warp instruction.
+//   * selectors are fetched as one 4-byte load per lane (the reference does one byte load
+//     per lane per edge), CSR indices/values as coalesced 128-byte streaming loads.
+//   * output zero-fill is part of the call (cudaMemsetAsync on the stream), rows are
+//     scheduled dynamically, long rows are spread over a whole CTA.
+#include "maxk_common.cuh"
+
+namespace maxk {
+
+constexpr int kBwdThreads = 256;
+constexpr int kBwdWarps = kBwdThreads / 32;
+constexpr int kBwdLongThreads = 512;
+constexpr int kBwdLongWarps = kBwdLongThreads / 32;
+constexpr unsigned kFullB = 0xffffffffu;
+
+// Stage one row of g into the warp's shared-memory slot (dim <= 256), fused division.
+__device__ __forceinline__ void stage_row(const float *__restrict__ g_row, float *gsm, int dim, bool has_div, float div)
+{
+    const int lane = lane_id();
+    if (dim == kAccDim) {
+        float4 a0 = ld_stream_f32x4(g_row + 4 * lane);
+        float4 a1 = ld_stream_f32x4(g_row + 128 + 4 * lane);
+        if (has_div) {
+            a0.x /= div; a0.y /= div; a0.z /= div; a0.w /= div;
+            a1.x /= div; a1.y /= div; a1.z /= div; a1.w /= div;
+        }
+        reinterpret_cast<float4 *>(gsm)[lane] = a0;
+        reinterpret_cast<float4 *>(gsm)[32 + lane] = a1;
+    } else {
+        for (int j = lane; j < kAccDim; j += 32) {
+            float a = j < dim ? g_row[j] : 0.f;
+            if (has_div) a /= div;
+            gsm[j] = a;
+        }
+    }
+    __syncwarp();
+}
+
+// K % 4 == 0, K <= 128: LPE = K/4 lanes per edge, EPI = 128/K edges per warp instruction.
+template <int K, int UNROLL>
+__device__ __forceinline__ void scatter_vec4(const int *__restrict__ idx, const float *__restrict__ val,
+                                             const uint8_t *__restrict__ csel, float *__restrict__ gs,
+                                             const float *gsm, int b, int e, int batch0, int stride)
+{
+    constexpr int LPE = K / 4;
+    constexpr int EPI = 32 / LPE;
+    const int lane = lane_id();
+    const int q = lane / LPE, t = lane % LPE;
+
+    int base = b + batch0 * 32;
+    int nxt_c = 0;
+    float nxt_w = 0.f;
+    if (base + lane < e) {
+        nxt_c = ld_stream_i32(idx + base + lane);
+        nxt_w = ld_stream_f32(val + base + lane);
+    }
+    for (; base < e; base += stride * 32) {
+        const int n = min(32, e - base);
+        const int my_c = nxt_c;
+        const float my_w = nxt_w;
+        const int nb = base + stride * 32;
+        nxt_c = 0;
+        nxt_w = 0.f;
+        if (nb + lane < e) {
+            nxt_c = ld_stream_i32(idx + nb + lane);
+            nxt_w = ld_stream_f32(val + nb + lane);
+        }
+        for (int j = 0; j < n; j += EPI * UNROLL) {
+            uint32_t s4[UNROLL];
+            float w[UNROLL];
+            size_t off[UNROLL];
+            bool ok[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int ej = j + u * EPI + q;
+                const int c = __shfl_sync(kFullB, my_c, ej & 31);
+                w[u] = __shfl_sync(kFullB, my_w, ej & 31);
+                ok[u] = ej < n;
+                off[u] = (size_t)c * K + 4 * t;
+                s4[u] = 0;
+                if (ok[u]) s4[u] = __ldg(reinterpret_cast<const uint32_t *>(csel + off[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (ok[u]) {
+                    const float x0 = w[u] * gsm[s4[u] & 0xff];
+                    const float x1 = w[u] * gsm[(s4[u] >> 8) & 0xff];
+                    const float x2 = w[u] * gsm[(s4[u] >> 16) & 0xff];
+                    const float x3 = w[u] * gsm[s4[u] >> 24];
+                    red_add_f32x4(gs + off[u], x0, x1, x2, x3);
+                }
+            }
+        }
+    }
+}
+
+// any k: scalar reductions, one edge per step.
+__device__ __forceinline__ void scatter_any_k(const int *__restrict__ idx, const float *__restrict__ val,
+                                              const uint8_t *__restrict__ csel, float *__restrict__ gs,
+                                              const float *gsm, int k, int b, int e, int batch0, int stride)
+{
+    const int lane = lane_id();
+    for (int base = b + batch0 * 32; base < e; base += stride * 32) {
+        const int n = min(32, e - base);
+        int my_c = 0;
+        float my_w = 0.f;
+        if (lane < n) {
+            my_c = ld_stream_i32(idx + base + lane);
+            my_w = ld_stream_f32(val + base + lane);
+        }
+        for (int j = 0; j < n; ++j) {
+            const int c = __shfl_sync(kFullB, my_c, j);
+            const float w = __shfl_sync(kFullB, my_w, j);
+            for (int l = lane; l < k; l += 32) {
+                const size_t off = (size_t)c * k + l;
+                atomicAdd(gs + off, w * gsm[__ldg(csel + off)]);
+            }
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void scatter_row(const int *idx, const float *val, const uint8_t *csel, float *gs,
+                                            const float *gsm, int k, int b, int e, int batch0, int stride)
+{
+    if constexpr (K == 8) scatter_vec4<8, 2>(idx, val, csel, gs, gsm, b, e, batch0, stride);
+    else if constexpr (K == 16) scatter_vec4<16, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
+    else if constexpr (K == 32) scatter_vec4<32, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
+    else if constexpr (K == 64) scatter_vec4<64, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
+    else scatter_any_k(idx, val, csel, gs, gsm, k, b, e, batch0, stride);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBwdThreads, 4)
+sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_end,
+                 const int *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ g,
+                 const uint8_t *__restrict__ csel, float *__restrict__ gs, int n_rows, int dim, int k,
+                 const float *__restrict__ row_div, SchedWorkspace *ws, int *__restrict__ long_rows,
+                 int rows_per_grab)
+{
+    __shared__ __align__(16) float smem[kBwdWarps * kAccDim];
+    const int lane = lane_id();
+    float *gsm = smem + (threadIdx.x >> 5) * kAccDim;
+    for (;;) {
+        int first = 0;
+        if (lane == 0) first = atomicAdd(&ws->row_counter, rows_per_grab);
+        first = __shfl_sync(kFullB, first, 0);
+        if (first >= n_rows) break;
+        const int nr = min(rows_per_grab, n_rows - first);
+        int rb = 0, re = 0;
+        if (lane < nr) {
+            rb = __ldg(row_begin + first + lane);
+            re = __ldg(row_end + first + lane);
+        }
+        for (int i = 0; i < nr; ++i) {
+            const int r = first + i;
+            const int b = __shfl_sync(kFullB, rb, i), e = __shfl_sync(kFullB, re, i);
+            if (e <= b) continue;
+            if (e - b > kLongRow) {
+                if (lane == 0) long_rows[atomicAdd(&ws->long_count, 1)] = r;
+                continue;
+            }
+            const bool has_div = row_div != nullptr;
+            __syncwarp();
+            stage_row(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
+            scatter_row<K>(idx, val, csel, gs, gsm, k, b, e, 0, 1);
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBwdLongThreads, 1)
+sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_end,
+                      const int *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ g,
+                      const uint8_t *__restrict__ csel, float *__restrict__ gs, int dim, int k,
+                      const float *__restrict__ row_div, SchedWorkspace *ws, const int *__restrict__ long_rows)
+{
+    __shared__ __align__(16) float smem[kBwdLongWarps * kAccDim];
+    __shared__ int s_item;
+    const int warp = threadIdx.x >> 5;
+    float *gsm = smem + warp * kAccDim;
+    const int n_long = ws->long_count;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(&ws->long_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_long) break;
+        const int r = long_rows[item];
+        const int b = row_begin[r], e = row_end[r];
+        const bool has_div = row_div != nullptr;
+        stage_row(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
+        scatter_row<K>(idx, val, csel, gs, gsm, k, b, e, warp, kBwdLongWarps);
+    }
+}
+
+int pick_rows_per_grab(int64_t n_rows, int64_t n_edges, int total_warps);  // spgemm_fwd.cu
+
+template <int K>
+static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const int *idx, const float *val,
+                              const float *g, const uint8_t *csel, float *gs, int64_t n_rows, int64_t n_dst,
+                              int64_t n_edges, int dim, int k, const float *row_div, SchedWorkspace *ws,
+                              cudaStream_t stream)
+{
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    static int sms = kNumSMsB200;
+    if (!configured) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sspmm_bwd_kernel<K>, kBwdThreads, 0);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    int *long_rows = reinterpret_cast<int *>(ws + 1);
+    cudaError_t err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
+    if (err != cudaSuccess) return err;
+    err = cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream);
+    if (err != cudaSuccess) return err;
+    const int grid = sms * blocks_per_sm;
+    const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kBwdWarps);
+    sspmm_bwd_kernel<K><<<grid, kBwdThreads, 0, stream>>>(row_begin, row_end, idx, val, g, csel, gs, (int)n_rows, dim,
+                                                          k, row_div, ws, long_rows, rpg);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    sspmm_bwd_long_kernel<K><<<sms, kBwdLongThreads, 0, stream>>>(row_begin, row_end, idx, val, g, csel, gs, dim, k,
+                                                                  row_div, ws, long_rows);
+    return cudaGetLastError();
+}
+
+}  // namespace maxk
+
+using namespace maxk;
+
+extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_end, const int32_t *indices,
+                                   const float *values, const float *g, const uint8_t *cbsr_sel, float *gs,
+                                   int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
+                                   const float *row_div, void *workspace, size_t workspace_bytes,
+                                   maxk_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
+    if (k < 1 || k > dim) return MAXK_ERR_BAD_K;
+    if (n_rows < 0 || n_dst < 0 || n_edges < 0 || n_rows > INT32_MAX || n_edges > INT32_MAX) return MAXK_ERR_SIZE;
+    if (n_dst == 0) return MAXK_OK;
+    if (!gs) return MAXK_ERR_NULL;
+    if (n_rows == 0 || n_edges == 0)
+        return status_from_cuda(cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream));
+    if (!row_begin || !row_end || !indices || !values || !g || !cbsr_sel || !workspace) return MAXK_ERR_NULL;
+    if (workspace_bytes < maxk_spgemm_workspace_bytes(n_rows)) return MAXK_ERR_WORKSPACE;
+    if (((uintptr_t)gs | (uintptr_t)g | (uintptr_t)workspace) & 15) return MAXK_ERR_ALIGN;
+    if ((k % 4 == 0) && ((uintptr_t)cbsr_sel & 3)) return MAXK_ERR_ALIGN;
+    SchedWorkspace *ws = reinterpret_cast<SchedWorkspace *>(workspace);
+    cudaError_t err;
+    switch (k) {
+        case 8: err = launch_bwd<8>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
+        case 16: err = launch_bwd<16>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
+        case 32: err = launch_bwd<32>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
+        case 64: err = launch_bwd<64>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
+        default: err = launch_bwd<0>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
+    }
+    return status_from_cuda(err);
+}

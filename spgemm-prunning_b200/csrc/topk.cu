@@ -1,0 +1,329 @@
+// topk.cu -- MaxK row-wise top-k -> CBSR, plus the dense helpers of the MaxK nonlinearity (sm_100a).
+//
+// Replaces torch.topk(x, k, dim=1) + .to(uint8) on the reference's training path
+// (maxk_spgemm_function.py:53-57, model_integrated_v3.py:28-37) and the uint8 `topk` kernel
+// (kernels/maxk_kernel.cu:23-96), which quantises to 8 bits, emits the FIRST k elements above a
+// pivot rather than the top k and is hard-wired to k = 32.
+//
+// One warp per row, the row lives in registers (8 values per lane for dim = 256, loaded as two
+// coalesced float4).  Exact selection:
+//   1. keys  = order-preserving uint32 image of the floats (NaN largest, -0 == +0);
+//   2. T     = k-th largest key by a 32-step bitwise radix descent (warp REDUX per step);
+//   3. every key > T is selected; of the keys == T the lowest columns are taken until k
+//      (ballot-free: per-lane counts + warp exclusive scans in column order);
+//   4. entries are emitted in column order (MAXK_ORDER_COLUMN_ASC) or rank-sorted by
+//      (value desc, column asc) through shared memory (MAXK_ORDER_VALUE_DESC = torch order).
+// The same pass can write the dense masked row (the MaxK nonlinearity output), so the
+// reference's topk + zeros_like + scatter_ + multiply (4 dense passes) is one read + one write.
+#include "maxk_common.cuh"
+
+namespace maxk {
+
+constexpr int kTopkThreads = 256;
+constexpr int kTopkWarps = kTopkThreads / 32;
+constexpr unsigned kFullT = 0xffffffffu;
+
+__device__ __forceinline__ int warp_excl_scan(int v, int &total)
+{
+    const int lane = lane_id();
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(kFullT, inc, d);
+        if (lane >= d) inc += n;
+    }
+    total = __shfl_sync(kFullT, inc, 31);
+    return inc - v;
+}
+
+// Column owned by (lane, slot): slots 0-3 -> 4*lane+slot, slots 4-7 -> 128+4*lane+(slot-4).
+__device__ __forceinline__ int col_of(int lane, int slot) { return (slot < 4 ? 0 : 128) + 4 * lane + (slot & 3); }
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, int order,
+                 float *__restrict__ out_val, uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32,
+                 int64_t *__restrict__ out_i64, float *__restrict__ masked)
+{
+    __shared__ uint32_t s_key[kTopkWarps][kAccDim];
+    __shared__ float s_val[kTopkWarps][kAccDim];
+    __shared__ uint8_t s_col[kTopkWarps][kAccDim];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
+
+    for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
+        const float *row = x + r * dim;
+        float v[8];
+        if (dim == kAccDim) {
+            const float4 a = ld_stream_f32x4(row + 4 * lane);
+            const float4 b = ld_stream_f32x4(row + 128 + 4 * lane);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int c = col_of(lane, s);
+                v[s] = c < dim ? row[c] : 0.f;
+            }
+        }
+        uint32_t key[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) key[s] = (col_of(lane, s) < dim) ? order_key(v[s]) : 0u;  // pad: below every real key
+
+        // ---- k-th largest key: T = max{t : #(key >= t) >= k} -------------------------------
+        uint32_t T = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = T | (1u << bit);
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) cnt += (key[s] >= cand) ? 1 : 0;
+            cnt = __reduce_add_sync(kFullT, cnt);
+            if (cnt >= k) T = cand;
+        }
+
+        // ---- selection flags in column order ------------------------------------------------
+        int gt_lo = 0, gt_hi = 0, eq_lo = 0, eq_hi = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { gt_lo += key[s] > T; eq_lo += key[s] == T; }
+#pragma unroll
+        for (int s = 4; s < 8; ++s) { gt_hi += key[s] > T; eq_hi += key[s] == T; }
+        int tot_eq_lo, tot_eq_hi, tot_gt_lo, tot_gt_hi;
+        const int eq_before_lo = warp_excl_scan(eq_lo, tot_eq_lo);
+        const int eq_before_hi = warp_excl_scan(eq_hi, tot_eq_hi) + tot_eq_lo;
+        (void)tot_eq_hi;
+        const int gt_total = __reduce_add_sync(kFullT, gt_lo + gt_hi);
+        const int need_eq = k - gt_total;  // >= 1 by construction of T
+
+        bool selb[8];
+        int sel_lo = 0, sel_hi = 0;
+        {
+            int eq_rank = eq_before_lo;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const bool is_eq = key[s] == T;
+                selb[s] = (key[s] > T) || (is_eq && eq_rank < need_eq);
+                eq_rank += is_eq;
+                sel_lo += selb[s];
+            }
+            eq_rank = eq_before_hi;
+#pragma unroll
+            for (int s = 4; s < 8; ++s) {
+                const bool is_eq = key[s] == T;
+                selb[s] = (key[s] > T) || (is_eq && eq_rank < need_eq);
+                eq_rank += is_eq;
+                sel_hi += selb[s];
+            }
+        }
+        const int pos_lo = warp_excl_scan(sel_lo, tot_gt_lo);            // tot_gt_lo = #selected in low half
+        const int pos_hi = warp_excl_scan(sel_hi, tot_gt_hi) + tot_gt_lo;
+        (void)tot_gt_hi;
+
+        if (masked != nullptr) {
+            float *mrow = masked + r * dim;
+            if (dim == kAccDim) {
+                st_stream_f32x4(mrow + 4 * lane, make_float4(selb[0] ? v[0] : 0.f, selb[1] ? v[1] : 0.f,
+                                                            selb[2] ? v[2] : 0.f, selb[3] ? v[3] : 0.f));
+                st_stream_f32x4(mrow + 128 + 4 * lane, make_float4(selb[4] ? v[4] : 0.f, selb[5] ? v[5] : 0.f,
+                                                                  selb[6] ? v[6] : 0.f, selb[7] ? v[7] : 0.f));
+            } else {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int c = col_of(lane, s);
+                    if (c < dim) mrow[c] = selb[s] ? v[s] : 0.f;
+                }
+            }
+        }
+
+        // ---- compact the k selected entries (column order) into shared memory -----------------
+        {
+            int p = pos_lo;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (selb[s]) { s_val[warp][p] = v[s]; s_key[warp][p] = key[s]; s_col[warp][p] = (uint8_t)col_of(lane, s); ++p; }
+            p = pos_hi;
+#pragma unroll
+            for (int s = 4; s < 8; ++s)
+                if (selb[s]) { s_val[warp][p] = v[s]; s_key[warp][p] = key[s]; s_col[warp][p] = (uint8_t)col_of(lane, s); ++p; }
+        }
+        __syncwarp();
+
+        for (int i = lane; i < k; i += 32) {
+            int dst = i;
+            if (order == MAXK_ORDER_VALUE_DESC) {
+                // rank sort: entries are in column order, so "earlier index" == "lower column"
+                const uint32_t ki = s_key[warp][i];
+                int rank = 0;
+                for (int j = 0; j < k; ++j) {
+                    const uint32_t kj = s_key[warp][j];
+                    rank += (kj > ki) || (kj == ki && j < i);
+                }
+                dst = rank;
+            }
+            const int64_t o = r * k + dst;
+            const int c = s_col[warp][i];
+            out_val[o] = s_val[warp][i];
+            if (out_sel) out_sel[o] = (uint8_t)c;
+            if (out_i32) out_i32[o] = c;
+            if (out_i64) out_i64[o] = c;
+        }
+        __syncwarp();
+    }
+}
+
+// dense[r, sel[r,l]] = vals[r,l], everything else 0 (one warp per row, row written once).
+__global__ void __launch_bounds__(kTopkThreads)
+cbsr_scatter_kernel(const float *__restrict__ vals, const uint8_t *__restrict__ sel, int64_t n_rows, int dim, int k,
+                    float *__restrict__ dense)
+{
+    __shared__ __align__(16) float s_row[kTopkWarps][kAccDim];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
+    for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
+        for (int j = lane; j < kAccDim; j += 32) s_row[warp][j] = 0.f;
+        __syncwarp();
+        for (int l = lane; l < k; l += 32) s_row[warp][sel[r * k + l]] = vals[r * k + l];
+        __syncwarp();
+        float *drow = dense + r * dim;
+        if (dim == kAccDim) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(s_row[warp]);
+            st_stream_f32x4(drow + 4 * lane, s4[lane]);
+            st_stream_f32x4(drow + 128 + 4 * lane, s4[32 + lane]);
+        } else {
+            for (int j = lane; j < dim; j += 32) drow[j] = s_row[warp][j];
+        }
+        __syncwarp();
+    }
+}
+
+// out[r,j] = in[r,j] if j selected else 0 (+ add_vals at the selected positions).
+__global__ void __launch_bounds__(kTopkThreads)
+mask_apply_kernel(const float *__restrict__ in, const uint8_t *__restrict__ sel, const float *__restrict__ add_vals,
+                  int64_t n_rows, int dim, int k, float *__restrict__ out)
+{
+    __shared__ __align__(16) float s_add[kTopkWarps][kAccDim];
+    __shared__ uint32_t s_mask[kTopkWarps][8];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
+    for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
+        if (lane < 8) s_mask[warp][lane] = 0u;
+        if (add_vals)
+            for (int j = lane; j < kAccDim; j += 32) s_add[warp][j] = 0.f;
+        __syncwarp();
+        for (int l = lane; l < k; l += 32) {
+            const int c = sel[r * k + l];
+            atomicOr(&s_mask[warp][c >> 5], 1u << (c & 31));
+            if (add_vals) s_add[warp][c] = add_vals[r * k + l];
+        }
+        __syncwarp();
+        const float *irow = in + r * dim;
+        float *orow = out + r * dim;
+        for (int j = lane; j < dim; j += 32) {
+            const bool on = (s_mask[warp][j >> 5] >> (j & 31)) & 1u;
+            float o = on ? irow[j] : 0.f;
+            if (add_vals && on) o += s_add[warp][j];
+            orow[j] = o;
+        }
+        __syncwarp();
+    }
+}
+
+// out = A_csr x dense (validation helper; one warp per row, lanes stride over the columns).
+__global__ void __launch_bounds__(kTopkThreads)
+dense_spmm_kernel(const int *__restrict__ indptr, const int *__restrict__ idx, const float *__restrict__ val,
+                  const float *__restrict__ dense, int64_t n_rows, int dim, float *__restrict__ out)
+{
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
+    for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
+        const int b = indptr[r], e = indptr[r + 1];
+        for (int j0 = 0; j0 < dim; j0 += 256) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int p = b; p < e; ++p) {
+                const float w = val[p];
+                const float *drow = dense + (size_t)idx[p] * dim + j0;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int j = lane + 32 * s;
+                    if (j0 + j < dim) acc[s] = fmaf(w, drow[j], acc[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int j = j0 + lane + 32 * s;
+                if (j < dim) out[r * dim + j] = acc[s];
+            }
+        }
+    }
+}
+
+static int grid_for_rows(int64_t n_rows)
+{
+    int dev = 0, sms = kNumSMsB200;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t need = (n_rows + kTopkWarps - 1) / kTopkWarps;
+    const int64_t cap = (int64_t)sms * 8;  // 8 CTAs of 256 threads per SM, grid-stride beyond that
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+}  // namespace maxk
+
+using namespace maxk;
+
+extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order, float *cbsr_val,
+                              uint8_t *cbsr_sel, int32_t *idx_i32, int64_t *idx_i64, float *masked,
+                              maxk_stream_t stream)
+{
+    if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
+    if (k < 1 || k > dim) return MAXK_ERR_BAD_K;
+    if (n_rows < 0) return MAXK_ERR_SIZE;
+    if (n_rows == 0) return MAXK_OK;
+    if (!x || !cbsr_val) return MAXK_ERR_NULL;
+    if (dim == kAccDim && (((uintptr_t)x | (uintptr_t)masked) & 15)) return MAXK_ERR_ALIGN;
+    topk_cbsr_kernel<<<grid_for_rows(n_rows), kTopkThreads, 0, (cudaStream_t)stream>>>(
+        x, n_rows, dim, k, order, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked);
+    return status_from_cuda(cudaGetLastError());
+}
+
+extern "C" int maxk_cbsr_scatter(const float *vals, const uint8_t *sel, int64_t n_rows, int dim, int k, float *dense,
+                                 maxk_stream_t stream)
+{
+    if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
+    if (k < 1 || k > dim) return MAXK_ERR_BAD_K;
+    if (n_rows < 0) return MAXK_ERR_SIZE;
+    if (n_rows == 0) return MAXK_OK;
+    if (!vals || !sel || !dense) return MAXK_ERR_NULL;
+    if (dim == kAccDim && ((uintptr_t)dense & 15)) return MAXK_ERR_ALIGN;
+    cbsr_scatter_kernel<<<grid_for_rows(n_rows), kTopkThreads, 0, (cudaStream_t)stream>>>(vals, sel, n_rows, dim, k,
+                                                                                          dense);
+    return status_from_cuda(cudaGetLastError());
+}
+
+extern "C" int maxk_mask_apply(const float *in, const uint8_t *sel, const float *add_vals, int64_t n_rows, int dim,
+                               int k, float *out, maxk_stream_t stream)
+{
+    if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
+    if (k < 1 || k > dim) return MAXK_ERR_BAD_K;
+    if (n_rows < 0) return MAXK_ERR_SIZE;
+    if (n_rows == 0) return MAXK_OK;
+    if (!in || !sel || !out) return MAXK_ERR_NULL;
+    mask_apply_kernel<<<grid_for_rows(n_rows), kTopkThreads, 0, (cudaStream_t)stream>>>(in, sel, add_vals, n_rows,
+                                                                                        dim, k, out);
+    return status_from_cuda(cudaGetLastError());
+}
+
+extern "C" int maxk_dense_spmm(const int32_t *indptr, const int32_t *indices, const float *values,
+                               const float *dense, int64_t n_rows, int dim, float *out, maxk_stream_t stream)
+{
+    if (dim < 1) return MAXK_ERR_BAD_DIM;
+    if (n_rows < 0) return MAXK_ERR_SIZE;
+    if (n_rows == 0) return MAXK_OK;
+    if (!indptr || !out) return MAXK_ERR_NULL;
+    dense_spmm_kernel<<<grid_for_rows(n_rows), kTopkThreads, 0, (cudaStream_t)stream>>>(indptr, indices, values,
+                                                                                        dense, n_rows, dim, out);
+    return status_from_cuda(cudaGetLastError());
+}
