@@ -33,7 +33,7 @@ extern "C" {
 
 /* Status codes: 0 ok, >0 a cudaError_t from the launch, <0 argument errors below. */
 #define MAXK_OK 0
-#define MAXK_ERR_BAD_K (-1)          /* k < 1 or k > dim                                   */
+#define MAXK_ERR_BAD_K (-1)          /* k < 1 or k > dim (top-k) / k > 256 (SpGEMM, SSpMM)  */
 #define MAXK_ERR_BAD_DIM (-2)        /* dim < 1 or dim > 256 (uint8 selector)  */
 #define MAXK_ERR_NULL (-3)           /* a required pointer is NULL                         */
 #define MAXK_ERR_WORKSPACE (-4)      /* workspace too small                                */
@@ -48,7 +48,10 @@ const char *maxk_status_string(int status);
 
 /* top-k output order */
 #define MAXK_ORDER_VALUE_DESC 0 /* (value desc, column asc): torch.topk(sorted=True) order */
-#define MAXK_ORDER_COLUMN_ASC 1 /* column ascending: cheapest, used by the fused layer     */
+#define MAXK_ORDER_COLUMN_ASC 1 /* column ascending                                        */
+#define MAXK_ORDER_BANKED 2     /* (column mod m, column) ascending, m = maxk_banked_modulus(k): the order
+                                   on which (2)/(3) have the fewest shared-memory bank conflicts; the
+                                   fused layer uses it.  Equal to COLUMN_ASC when m == 1.      */
 
 /*
  * (1) MaxK row-wise top-k -> CBSR.
@@ -65,6 +68,7 @@ const char *maxk_status_string(int status);
  *   masked     [n_rows, dim] fp32   (nullable; x with every non-selected entry set to 0 =
  *                                    the MaxK nonlinearity output, maxk_models_integrated.py:28-37)
  */
+int maxk_banked_modulus(int k); /* 4, 4, 8, 16 for k = 8, 16, 32, 64; 1 otherwise */
 int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
                    float *cbsr_val, uint8_t *cbsr_sel, int32_t *idx_i32, int64_t *idx_i64,
                    float *masked, maxk_stream_t stream);

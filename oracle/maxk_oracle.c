@@ -61,9 +61,11 @@ static int kc_cmp(const void *a, const void *b)
  *   out_val  [N, k] fp32   k largest of the row
  *   out_sel  [N, k] int32  their columns
  * order = 0: entries sorted (value desc, column asc)   -- torch.topk(sorted=True) order
- * order = 1: entries sorted by column ascending         -- the order our fused kernels emit
+ * order = 1: entries sorted by column ascending
+ * order = 2: entries sorted by (column mod bank_mod, column) -- the order our fused kernels emit
+ *            (a pure permutation of the same k entries; consumers are order independent)
  */
-void oracle_topk(const float *x, int64_t N, int D, int k, float *out_val, int32_t *out_sel, int order)
+void oracle_topk(const float *x, int64_t N, int D, int k, float *out_val, int32_t *out_sel, int order, int bank_mod)
 {
 #pragma omp parallel
     {
@@ -73,11 +75,13 @@ void oracle_topk(const float *x, int64_t N, int D, int k, float *out_val, int32_
             const float *row = x + r * D;
             for (int j = 0; j < D; ++j) { buf[j].key = order_key(row[j]); buf[j].col = j; }
             qsort(buf, (size_t)D, sizeof(kc_t), kc_cmp);
-            if (order == 1) {
-                /* re-sort the chosen k by column: simple insertion sort */
+            if (order == 1 || order == 2) {
+                /* re-sort the chosen k by (col mod m, col): simple insertion sort */
+                const int m = (order == 2 && bank_mod > 1) ? bank_mod : 1;
                 for (int i = 1; i < k; ++i) {
                     kc_t t = buf[i]; int j = i - 1;
-                    while (j >= 0 && buf[j].col > t.col) { buf[j + 1] = buf[j]; --j; }
+                    while (j >= 0 && (buf[j].col % m > t.col % m ||
+                                      (buf[j].col % m == t.col % m && buf[j].col > t.col))) { buf[j + 1] = buf[j]; --j; }
                     buf[j + 1] = t;
                 }
             }

@@ -63,13 +63,19 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def banked_modulus(k):
+    return {8: 4, 16: 4, 32: 8, 64: 16}.get(k, 1)
+
+
 def topk(x, k, order=0):
-    """(values fp32 [N,k], columns int32 [N,k]); order 0 = (value desc, col asc), 1 = column asc."""
+    """(values fp32 [N,k], columns int32 [N,k]); order 0 = (value desc, col asc), 1 = column asc,
+    2 = (col mod banked_modulus(k), col) asc."""
     x = _f32(x)
     n, d = x.shape
     vals = np.empty((n, k), np.float32)
     cols = np.empty((n, k), np.int32)
-    lib().oracle_topk(_p(x), ctypes.c_int64(n), ctypes.c_int(d), ctypes.c_int(k), _p(vals), _p(cols), ctypes.c_int(order))
+    lib().oracle_topk(_p(x), ctypes.c_int64(n), ctypes.c_int(d), ctypes.c_int(k), _p(vals), _p(cols), ctypes.c_int(order),
+                      ctypes.c_int(banked_modulus(k)))
     return vals, cols
 
 

@@ -9,6 +9,7 @@ namespace maxk {
 constexpr int kAccDim = 256;          // accumulator width: uint8 selectors address at most 256 columns
 constexpr int kNumSMsB200 = 148;
 constexpr int kLongRow = 4096;        // rows with more edges are handled by a whole CTA
+constexpr unsigned kFullMask = 0xffffffffu;
 
 // Workspace layout shared by forward and backward (see maxk_spgemm_workspace_bytes).
 struct SchedWorkspace {
@@ -18,6 +19,40 @@ struct SchedWorkspace {
     int pad;
     // followed by int long_rows[n_rows]
 };
+
+// ---------------------------------------------------------------------------------------------
+// Banked lane layout shared by the forward accumulator and the backward staged gradient row.
+//
+// The SM's LSU data pipe moves one 128-byte wavefront per clock and is the limiter of both
+// kernels (ncu: l1tex__data_pipe_lsu_wavefronts 96 % / 90 % of peak in the first version), so
+// the layout is chosen to minimise wavefronts per edge:
+//   * a lane owns EPL consecutive CBSR entries of one edge (one 16-byte value load + one 4-byte
+//     selector load for EPL = 4): L = k/EPL lanes cover an edge, EPI = 32/L edges per warp
+//     instruction.  A request now touches EPI full rows instead of one (the LDG request rate,
+//     not L2 bandwidth, capped the 4-byte-per-lane gather at 35 G rows/s vs 116 G rows/s).
+//   * every edge slot q has its own copy of the 256 columns, and copy q only lives in banks
+//     [q*L, q*L+L): word address of (column c, copy q) = (c / L) * 32 + q * L + (c % L).
+//     Lanes of different edge slots can therefore never collide, and inside a slot a conflict
+//     needs two of the slot's L lanes to hold columns with equal c % L.  The top-k kernel emits
+//     rows sorted by (c % L, c) (MAXK_ORDER_BANKED), which spreads each residue class over the
+//     EPL accumulate instructions as evenly as possible (McNaughton wrap-around).
+// k = 8 uses EPL = 2; any other k falls back to L = 32, one copy, natural layout (address = c).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+struct Lay {
+    static constexpr bool kFast = (K == 8 || K == 16 || K == 32 || K == 64);
+    static constexpr int EPL = kFast ? (K == 8 ? 2 : 4) : 1;   // entries per lane
+    static constexpr int L = kFast ? K / EPL : 32;             // lanes per edge == banks per copy
+    static constexpr int EPI = 32 / L;                         // edges per warp instruction == copies
+    static constexpr int kWords = (kAccDim / L) * 32;          // floats per warp (== EPI * 256)
+    __device__ static __forceinline__ int word(int col) { return (col / L) * 32 + (col % L); }  // + q * L
+};
+
+// bank-residue modulus used by MAXK_ORDER_BANKED for a given k (host + device)
+__host__ __device__ inline int banked_modulus(int k)
+{
+    return k == 8 ? 4 : k == 16 ? 4 : k == 32 ? 8 : k == 64 ? 16 : 1;
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -43,6 +78,10 @@ __device__ __forceinline__ float4 ld_stream_f32x4(const float *p)
     return v;
 }
 // Streaming stores for outputs that are not re-read by this kernel.
+__device__ __forceinline__ void st_stream_f32(float *p, float v)
+{
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ void st_stream_f32x4(float *p, float4 v)
 {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -67,5 +106,13 @@ __device__ __forceinline__ uint32_t order_key(float f)
 }
 
 inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? MAXK_OK : (int)e; }
+
+inline int device_sm_count()
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : kNumSMsB200;
+}
 
 }  // namespace maxk

@@ -3,20 +3,20 @@
 // Replaces spmm_kernel_opt2_sparse_v3 (reference kernels/spmm_maxk.cu:17-106).  Design
 // (DESIGN.md "Forward SpGEMM"):
 //   * one warp OWNS one output row: the whole edge list of the row is reduced by that warp
-//     into a private 256-float shared-memory accumulator and the row is written exactly
-//     once with 16-byte stores.  No global atomics, no output memset, fixed reduction
-//     order (the reference flushes 256 global atomics per <=64-edge segment,
-//     spmm_maxk.cu:101-105, into a torch::zeros output, cuda_kernel_bindings.cpp:71).
-//   * CSR indices/values are read as coalesced 128-byte streaming loads, 32 edges per
-//     warp instruction, and handed to the lanes by shuffles (the reference issues one
-//     scalar broadcast __ldg per edge, spmm_maxk.cu:72-73).
-//   * UNROLL independent neighbour-row gathers are in flight per warp before the first
-//     accumulate, so the idx -> CBSR row -> accumulator chain is pipelined.
-//   * k < 32 packs 32/k edges into one warp instruction, each edge slot with its own
-//     accumulator copy, so all 32 lanes work for every k (the reference idles
-//     1 - k/32 of its warps, spmm_maxk.cu:27,64).
-//   * rows are handed out dynamically (one global counter), rows longer than kLongRow
-//     are deferred to a whole-CTA kernel, so skewed graphs do not serialise on one warp.
+//     into private shared-memory accumulators and the row is written exactly once.  No global
+//     atomics, no output memset, fixed reduction order (the reference flushes 256 global
+//     atomics per <=64-edge segment, spmm_maxk.cu:101-105, into a torch::zeros output,
+//     cuda_kernel_bindings.cpp:71).
+//   * CSR indices/values are read as coalesced 128-byte streaming loads, 32 edges per warp
+//     instruction, prefetched one batch ahead, and handed to the lanes by shuffles (the
+//     reference issues one scalar broadcast __ldg per edge, spmm_maxk.cu:72-73).
+//   * neighbour CBSR rows are gathered with 16-byte loads, EPI = 128/k whole rows per warp
+//     instruction, UNROLL instructions in flight before the first accumulate; the accumulators
+//     use the banked per-edge-slot layout of maxk_common.cuh (Lay<K>), which keeps the LSU
+//     data pipe -- the measured limiter -- at the fewest wavefronts per edge.  All 32 lanes work
+//     for every k (the reference idles 1 - k/32 of its warps for k < 32, spmm_maxk.cu:27,64).
+//   * rows are handed out dynamically (one global counter), rows longer than kLongRow are
+//     deferred to a whole-CTA kernel, so skewed graphs do not serialise on one warp.
 //   * the degree normalisation the reference does in a separate PyTorch pass
 //     (maxk_spgemm_function.py:86) is fused into the row epilogue.
 #include "maxk_common.cuh"
@@ -27,22 +27,43 @@ constexpr int kFwdThreads = 256;
 constexpr int kFwdWarps = kFwdThreads / 32;
 constexpr int kLongThreads = 512;
 constexpr int kLongWarps = kLongThreads / 32;
-constexpr unsigned kFull = 0xffffffffu;
+
+template <int EPL> struct EntryLoad;
+template <> struct EntryLoad<4> {
+    float v[4];
+    uint32_t s;
+    __device__ __forceinline__ void load(const float *cval, const uint8_t *csel, size_t off)
+    {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(cval + off));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        s = __ldg(reinterpret_cast<const uint32_t *>(csel + off));
+    }
+};
+template <> struct EntryLoad<2> {
+    float v[2];
+    uint32_t s;
+    __device__ __forceinline__ void load(const float *cval, const uint8_t *csel, size_t off)
+    {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(cval + off));
+        v[0] = t.x; v[1] = t.y;
+        s = __ldg(reinterpret_cast<const unsigned short *>(csel + off));
+    }
+};
 
 // ---------------------------------------------------------------------------------
 // Edge accumulation for one row segment [b, e), visiting 32-edge batches
-// batch0, batch0+stride, ...  K = compile-time k (8/16/32), EPI = 32/K edges per instruction.
+// batch0, batch0+stride, ...   Fast path: k in {8, 16, 32, 64}.
 // ---------------------------------------------------------------------------------
 template <int K, int UNROLL>
-__device__ __forceinline__ void accumulate_small_k(const int *__restrict__ idx, const float *__restrict__ val,
-                                                   const float *__restrict__ cval,
-                                                   const uint8_t *__restrict__ csel, float *acc, int b, int e,
-                                                   int batch0, int stride)
+__device__ __forceinline__ void accumulate_fast(const int *__restrict__ idx, const float *__restrict__ val,
+                                                const float *__restrict__ cval, const uint8_t *__restrict__ csel,
+                                                float *acc, int b, int e, int batch0, int stride)
 {
-    constexpr int EPI = 32 / K;
+    using LY = Lay<K>;
+    constexpr int EPL = LY::EPL, L = LY::L, EPI = LY::EPI;
     const int lane = lane_id();
-    const int grp = lane / K, pos = lane % K;
-    float *acc_g = acc + grp * kAccDim;
+    const int q = lane / L, t = lane % L;
+    float *acc_q = acc + q * L;
 
     int base = b + batch0 * 32;
     int nxt_c = 0;
@@ -63,88 +84,40 @@ __device__ __forceinline__ void accumulate_small_k(const int *__restrict__ idx, 
             nxt_w = ld_stream_f32(val + nb + lane);
         }
         for (int j = 0; j < n; j += EPI * UNROLL) {
-            float v[UNROLL], w[UNROLL];
-            int s[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int ej = j + u * EPI + grp;
-                const int c = __shfl_sync(kFull, my_c, ej & 31);
-                w[u] = __shfl_sync(kFull, my_w, ej & 31);
-                s[u] = -1;
-                v[u] = 0.f;
-                if (ej < n) {
-                    const size_t off = (size_t)c * K + pos;
-                    v[u] = __ldg(cval + off);
-                    s[u] = __ldg(csel + off);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                // columns are distinct within a CBSR row and every edge slot has its own
-                // accumulator copy, so this read-modify-write has no intra-instruction conflict
-                if (s[u] >= 0) acc_g[s[u]] = fmaf(w[u], v[u], acc_g[s[u]]);
-                __syncwarp();
-            }
-        }
-    }
-}
-
-// k == 64: two entries per lane (8-byte value load, 2-byte selector load), one edge per instruction.
-template <int UNROLL>
-__device__ __forceinline__ void accumulate_k64(const int *__restrict__ idx, const float *__restrict__ val,
-                                               const float *__restrict__ cval, const uint8_t *__restrict__ csel,
-                                               float *acc, int b, int e, int batch0, int stride)
-{
-    const int lane = lane_id();
-    int base = b + batch0 * 32;
-    int nxt_c = 0;
-    float nxt_w = 0.f;
-    if (base + lane < e) {
-        nxt_c = ld_stream_i32(idx + base + lane);
-        nxt_w = ld_stream_f32(val + base + lane);
-    }
-    for (; base < e; base += stride * 32) {
-        const int n = min(32, e - base);
-        const int my_c = nxt_c;
-        const float my_w = nxt_w;
-        const int nb = base + stride * 32;
-        nxt_c = 0;
-        nxt_w = 0.f;
-        if (nb + lane < e) {
-            nxt_c = ld_stream_i32(idx + nb + lane);
-            nxt_w = ld_stream_f32(val + nb + lane);
-        }
-        for (int j = 0; j < n; j += UNROLL) {
-            float2 v[UNROLL];
+            EntryLoad<EPL> ent[UNROLL];
             float w[UNROLL];
-            int s[UNROLL];
+            bool ok[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const int ej = j + u;
-                const int c = __shfl_sync(kFull, my_c, ej & 31);
-                w[u] = __shfl_sync(kFull, my_w, ej & 31);
-                s[u] = -1;
-                v[u] = make_float2(0.f, 0.f);
-                if (ej < n) {
-                    const size_t off = (size_t)c * 64 + 2 * lane;
-                    v[u] = __ldg(reinterpret_cast<const float2 *>(cval + off));
-                    s[u] = __ldg(reinterpret_cast<const unsigned short *>(csel + off));
-                }
+                const int ej = j + u * EPI + q;
+                const int c = __shfl_sync(kFullMask, my_c, ej & 31);
+                w[u] = __shfl_sync(kFullMask, my_w, ej & 31);
+                ok[u] = ej < n;
+                if (ok[u]) ent[u].load(cval, csel, (size_t)c * K + EPL * t);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                if (s[u] >= 0) {
-                    const int s0 = s[u] & 0xff, s1 = s[u] >> 8;
-                    acc[s0] = fmaf(w[u], v[u].x, acc[s0]);
-                    acc[s1] = fmaf(w[u], v[u].y, acc[s1]);
+                if (ok[u]) {
+                    // the EPL columns of a lane and the columns of the other lanes of this edge
+                    // slot are all distinct (one CBSR row), other slots use other banks: the
+                    // EPL read-modify-writes are independent, so read all, then write all.
+                    int o[EPL];
+                    float a[EPL];
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) {
+                        o[i] = LY::word((ent[u].s >> (8 * i)) & 0xff);
+                        a[i] = acc_q[o[i]];
+                    }
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) acc_q[o[i]] = fmaf(w[u], ent[u].v[i], a[i]);
                 }
-                __syncwarp();
+                __syncwarp();  // next step may touch the same column of the same copy from another lane
             }
         }
     }
 }
 
-// any k in [1, 256]: one edge per step, lanes stride over the k entries.
+// any k in [1, 256]: one edge per step, lanes stride over the k entries (natural layout, one copy).
 __device__ __forceinline__ void accumulate_any_k(const int *__restrict__ idx, const float *__restrict__ val,
                                                  const float *__restrict__ cval, const uint8_t *__restrict__ csel,
                                                  float *acc, int k, int b, int e, int batch0, int stride)
@@ -159,8 +132,8 @@ __device__ __forceinline__ void accumulate_any_k(const int *__restrict__ idx, co
             my_w = ld_stream_f32(val + base + lane);
         }
         for (int j = 0; j < n; ++j) {
-            const int c = __shfl_sync(kFull, my_c, j);
-            const float w = __shfl_sync(kFull, my_w, j);
+            const int c = __shfl_sync(kFullMask, my_c, j);
+            const float w = __shfl_sync(kFullMask, my_w, j);
             for (int l = lane; l < k; l += 32) {
                 const size_t off = (size_t)c * k + l;
                 const int s = __ldg(csel + off);
@@ -172,60 +145,49 @@ __device__ __forceinline__ void accumulate_any_k(const int *__restrict__ idx, co
 }
 
 template <int K>
-struct FwdTraits {
-    static constexpr int kCopies = (K >= 8 && K <= 32) ? 32 / K : 1;  // accumulator copies per warp
-};
-
-template <int K>
 __device__ __forceinline__ void accumulate_row(const int *idx, const float *val, const float *cval,
                                                const uint8_t *csel, float *acc, int k, int b, int e, int batch0,
                                                int stride)
 {
-    if constexpr (K == 32) accumulate_small_k<32, 8>(idx, val, cval, csel, acc, b, e, batch0, stride);
-    else if constexpr (K == 16) accumulate_small_k<16, 8>(idx, val, cval, csel, acc, b, e, batch0, stride);
-    else if constexpr (K == 8) accumulate_small_k<8, 8>(idx, val, cval, csel, acc, b, e, batch0, stride);
-    else if constexpr (K == 64) accumulate_k64<4>(idx, val, cval, csel, acc, b, e, batch0, stride);
+    if constexpr (Lay<K>::kFast) accumulate_fast<K, 4>(idx, val, cval, csel, acc, b, e, batch0, stride);
     else accumulate_any_k(idx, val, cval, csel, acc, k, b, e, batch0, stride);
 }
 
-// Row epilogue of the warp-owned path: sum the accumulator copies, re-zero them, apply the
-// fused divisor and write the row once.
-template <int COPIES>
+// Column `col` summed over the EPI copies of `n_sets` accumulator sets (sets are kWords apart),
+// read with a lane-skewed copy order so that the 32 lanes hit 32 different banks.
+template <int K>
+__device__ __forceinline__ float sum_copies(const float *acc, int col, int lane, int n_sets)
+{
+    using LY = Lay<K>;
+    const int w0 = LY::word(col);
+    float a = 0.f;
+    for (int s = 0; s < n_sets; ++s) {
+#pragma unroll
+        for (int q = 0; q < LY::EPI; ++q) {
+            const int qq = (q + lane / LY::L) % LY::EPI;
+            a += acc[s * LY::kWords + w0 + qq * LY::L];
+        }
+    }
+    return a;
+}
+
+// Row epilogue of the warp-owned path: sum the copies, re-zero them, fused divisor, one write.
+template <int K>
 __device__ __forceinline__ void write_row(float *acc, float *__restrict__ out_row, int dim, bool has_div, float div)
 {
+    using LY = Lay<K>;
     const int lane = lane_id();
+    float o[kAccDim / 32];
+#pragma unroll
+    for (int n = 0; n < kAccDim / 32; ++n) o[n] = sum_copies<K>(acc, lane + 32 * n, lane, 1);
+    __syncwarp();
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
-    if (dim == kAccDim) {
-        float4 a0 = acc4[lane], a1 = acc4[32 + lane];
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        acc4[lane] = z;
-        acc4[32 + lane] = z;
 #pragma unroll
-        for (int g = 1; g < COPIES; ++g) {
-            const float4 b0 = acc4[g * 64 + lane], b1 = acc4[g * 64 + 32 + lane];
-            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
-            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
-            acc4[g * 64 + lane] = z;
-            acc4[g * 64 + 32 + lane] = z;
-        }
-        if (has_div) {
-            a0.x /= div; a0.y /= div; a0.z /= div; a0.w /= div;
-            a1.x /= div; a1.y /= div; a1.z /= div; a1.w /= div;
-        }
-        st_stream_f32x4(out_row + 4 * lane, a0);
-        st_stream_f32x4(out_row + 128 + 4 * lane, a1);
-    } else {
-        for (int j = lane; j < kAccDim; j += 32) {
-            float a = acc[j];
-            acc[j] = 0.f;
+    for (int i = 0; i < LY::kWords / 128; ++i) acc4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int g = 1; g < COPIES; ++g) {
-                a += acc[g * kAccDim + j];
-                acc[g * kAccDim + j] = 0.f;
-            }
-            if (has_div) a /= div;
-            if (j < dim) out_row[j] = a;
-        }
+    for (int n = 0; n < kAccDim / 32; ++n) {
+        const int col = lane + 32 * n;
+        if (col < dim) st_stream_f32(out_row + col, has_div ? o[n] / div : o[n]);
     }
     __syncwarp();
 }
@@ -241,17 +203,17 @@ spgemm_fwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row
                   int n_rows, int dim, int k, const float *__restrict__ row_div, SchedWorkspace *ws,
                   int *__restrict__ long_rows, int rows_per_grab)
 {
-    constexpr int COPIES = FwdTraits<K>::kCopies;
+    using LY = Lay<K>;
     extern __shared__ __align__(16) float smem[];
     const int lane = lane_id();
-    float *acc = smem + (threadIdx.x >> 5) * (COPIES * kAccDim);
-    for (int i = lane; i < COPIES * kAccDim; i += 32) acc[i] = 0.f;
+    float *acc = smem + (threadIdx.x >> 5) * LY::kWords;
+    for (int i = lane; i < LY::kWords; i += 32) acc[i] = 0.f;
     __syncwarp();
 
     for (;;) {
         int first = 0;
         if (lane == 0) first = atomicAdd(&ws->row_counter, rows_per_grab);
-        first = __shfl_sync(kFull, first, 0);
+        first = __shfl_sync(kFullMask, first, 0);
         if (first >= n_rows) break;
         const int nr = min(rows_per_grab, n_rows - first);
         int rb = 0, re = 0;
@@ -261,14 +223,14 @@ spgemm_fwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row
         }
         for (int i = 0; i < nr; ++i) {
             const int r = first + i;
-            const int b = __shfl_sync(kFull, rb, i), e = __shfl_sync(kFull, re, i);
+            const int b = __shfl_sync(kFullMask, rb, i), e = __shfl_sync(kFullMask, re, i);
             if (e - b > kLongRow) {
                 if (lane == 0) long_rows[atomicAdd(&ws->long_count, 1)] = r;
                 continue;
             }
             if (e > b) accumulate_row<K>(idx, val, cval, csel, acc, k, b, e, 0, 1);
             const bool has_div = row_div != nullptr;
-            write_row<COPIES>(acc, out + (size_t)r * dim, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
+            write_row<K>(acc, out + (size_t)r * dim, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
         }
     }
 }
@@ -285,12 +247,12 @@ spgemm_fwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict_
                        int dim, int k, const float *__restrict__ row_div, SchedWorkspace *ws,
                        const int *__restrict__ long_rows)
 {
-    constexpr int COPIES = FwdTraits<K>::kCopies;
+    using LY = Lay<K>;
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_item;
     const int warp = threadIdx.x >> 5;
-    float *acc = smem + warp * (COPIES * kAccDim);
-    for (int i = threadIdx.x; i < kLongWarps * COPIES * kAccDim; i += kLongThreads) smem[i] = 0.f;
+    float *acc = smem + warp * LY::kWords;
+    for (int i = threadIdx.x; i < kLongWarps * LY::kWords; i += kLongThreads) smem[i] = 0.f;
     const int n_long = ws->long_count;
     for (;;) {
         __syncthreads();
@@ -302,14 +264,13 @@ spgemm_fwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict_
         const int b = row_begin[r], e = row_end[r];
         accumulate_row<K>(idx, val, cval, csel, acc, k, b, e, warp, kLongWarps);
         __syncthreads();
-        for (int j = threadIdx.x; j < kAccDim; j += kLongThreads) {
-            float a = 0.f;
-            for (int w = 0; w < kLongWarps * COPIES; ++w) {
-                a += smem[w * kAccDim + j];
-                smem[w * kAccDim + j] = 0.f;
-            }
-            if (row_div != nullptr) a /= row_div[r];
-            if (j < dim) out[(size_t)r * dim + j] = a;
+        float o = 0.f;
+        if (threadIdx.x < kAccDim) o = sum_copies<K>(smem, threadIdx.x, threadIdx.x & 31, kLongWarps);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLongWarps * LY::kWords; i += kLongThreads) smem[i] = 0.f;
+        if (threadIdx.x < dim) {
+            if (row_div != nullptr) o /= row_div[r];
+            out[(size_t)r * dim + threadIdx.x] = o;
         }
     }
 }
@@ -317,19 +278,6 @@ spgemm_fwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict_
 // ---------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------
-struct DeviceInfo {
-    int sms = 0;
-};
-static DeviceInfo device_info()
-{
-    DeviceInfo d;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-    if (d.sms <= 0) d.sms = kNumSMsB200;
-    return d;
-}
-
 int pick_rows_per_grab(int64_t n_rows, int64_t n_edges, int total_warps)
 {
     const int64_t avg = n_rows > 0 ? (n_edges + n_rows - 1) / n_rows : 1;
@@ -346,30 +294,31 @@ static cudaError_t launch_fwd(const int *row_begin, const int *row_end, const in
                               const float *cval, const uint8_t *csel, float *out, int64_t n_rows, int64_t n_edges,
                               int dim, int k, const float *row_div, SchedWorkspace *ws, cudaStream_t stream)
 {
-    constexpr int COPIES = FwdTraits<K>::kCopies;
-    const size_t smem_main = (size_t)kFwdWarps * COPIES * kAccDim * sizeof(float);
-    const size_t smem_long = (size_t)kLongWarps * COPIES * kAccDim * sizeof(float);
+    using LY = Lay<K>;
+    const size_t smem_main = (size_t)kFwdWarps * LY::kWords * sizeof(float);
+    const size_t smem_long = (size_t)kLongWarps * LY::kWords * sizeof(float);
     static bool configured = false;  // per template instance
     static int blocks_per_sm = 1;
+    static int sms = kNumSMsB200;
     if (!configured) {
         cudaFuncSetAttribute(spgemm_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main);
         cudaFuncSetAttribute(spgemm_fwd_long_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, spgemm_fwd_kernel<K>, kFwdThreads, smem_main);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
+        sms = device_sm_count();
         configured = true;
     }
-    const DeviceInfo di = device_info();
     int *long_rows = reinterpret_cast<int *>(ws + 1);
     cudaError_t err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
     if (err != cudaSuccess) return err;
-    const int grid = di.sms * blocks_per_sm;
+    const int grid = sms * blocks_per_sm;
     const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kFwdWarps);
     spgemm_fwd_kernel<K><<<grid, kFwdThreads, smem_main, stream>>>(row_begin, row_end, idx, val, cval, csel, out,
                                                                    (int)n_rows, dim, k, row_div, ws, long_rows, rpg);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    spgemm_fwd_long_kernel<K><<<di.sms, kLongThreads, smem_long, stream>>>(row_begin, row_end, idx, val, cval, csel,
-                                                                          out, dim, k, row_div, ws, long_rows);
+    spgemm_fwd_long_kernel<K><<<sms, kLongThreads, smem_long, stream>>>(row_begin, row_end, idx, val, cval, csel, out,
+                                                                       dim, k, row_div, ws, long_rows);
     return cudaGetLastError();
 }
 
@@ -390,13 +339,14 @@ extern "C" int maxk_spgemm_forward(const int32_t *row_begin, const int32_t *row_
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
-    if (k < 1 || k > dim) return MAXK_ERR_BAD_K;
+    if (k < 1 || k > kAccDim) return MAXK_ERR_BAD_K;
     if (n_rows < 0 || n_edges < 0 || n_rows > INT32_MAX || n_edges > INT32_MAX) return MAXK_ERR_SIZE;
     if (n_rows == 0) return MAXK_OK;
     if (!row_begin || !row_end || !out || !workspace) return MAXK_ERR_NULL;
     if (n_edges > 0 && (!indices || !values || !cbsr_val || !cbsr_sel)) return MAXK_ERR_NULL;
     if (workspace_bytes < maxk_spgemm_workspace_bytes(n_rows)) return MAXK_ERR_WORKSPACE;
-    if (((uintptr_t)out | (uintptr_t)cbsr_val | (uintptr_t)workspace) & 15) return MAXK_ERR_ALIGN;
+    if (((uintptr_t)cbsr_val | (uintptr_t)workspace) & 15) return MAXK_ERR_ALIGN;
+    if (((uintptr_t)cbsr_sel | (uintptr_t)out) & 3) return MAXK_ERR_ALIGN;
     SchedWorkspace *ws = reinterpret_cast<SchedWorkspace *>(workspace);
     cudaError_t err;
     switch (k) {

@@ -24,39 +24,50 @@ constexpr int kBwdLongThreads = 512;
 constexpr int kBwdLongWarps = kBwdLongThreads / 32;
 constexpr unsigned kFullB = 0xffffffffu;
 
-// Stage one row of g into the warp's shared-memory slot (dim <= 256), fused division.
+// Stage one row of g (dim <= 256, fused division) into the warp's shared-memory slot in the
+// banked layout of Lay<K>: every edge slot q gets its own copy living in banks [q*L, q*L+L), so
+// lanes of different edge slots never collide when they look their columns up.  The copies are
+// written in a lane-skewed order (32 distinct banks per store instruction).
+template <int K>
 __device__ __forceinline__ void stage_row(const float *__restrict__ g_row, float *gsm, int dim, bool has_div, float div)
 {
+    using LY = Lay<K>;
     const int lane = lane_id();
-    if (dim == kAccDim) {
-        float4 a0 = ld_stream_f32x4(g_row + 4 * lane);
-        float4 a1 = ld_stream_f32x4(g_row + 128 + 4 * lane);
-        if (has_div) {
-            a0.x /= div; a0.y /= div; a0.z /= div; a0.w /= div;
-            a1.x /= div; a1.y /= div; a1.z /= div; a1.w /= div;
-        }
-        reinterpret_cast<float4 *>(gsm)[lane] = a0;
-        reinterpret_cast<float4 *>(gsm)[32 + lane] = a1;
-    } else {
-        for (int j = lane; j < kAccDim; j += 32) {
-            float a = j < dim ? g_row[j] : 0.f;
-            if (has_div) a /= div;
-            gsm[j] = a;
-        }
+#pragma unroll
+    for (int n = 0; n < kAccDim / 32; ++n) {
+        const int col = lane + 32 * n;
+        float a = col < dim ? ld_stream_f32(g_row + col) : 0.f;
+        if (has_div) a /= div;
+        const int w0 = LY::word(col);
+#pragma unroll
+        for (int q = 0; q < LY::EPI; ++q) gsm[w0 + ((q + lane / LY::L) % LY::EPI) * LY::L] = a;
     }
     __syncwarp();
 }
 
-// K % 4 == 0, K <= 128: LPE = K/4 lanes per edge, EPI = 128/K edges per warp instruction.
+template <int EPL> struct SelLoad;
+template <> struct SelLoad<4> {
+    __device__ static __forceinline__ uint32_t load(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+    __device__ static __forceinline__ void red(float *p, const float *x) { red_add_f32x4(p, x[0], x[1], x[2], x[3]); }
+};
+template <> struct SelLoad<2> {
+    __device__ static __forceinline__ uint32_t load(const uint8_t *p) { return __ldg(reinterpret_cast<const unsigned short *>(p)); }
+    __device__ static __forceinline__ void red(float *p, const float *x) { red_add_f32x2(p, x[0], x[1]); }
+};
+
+// Fast path, k in {8, 16, 32, 64}: a lane owns EPL consecutive entries of one destination row,
+// L = k/EPL lanes cover an edge, EPI = 32/L edges per warp instruction; one vector reduction
+// (16 B, or 8 B for k = 8) per lane per edge.
 template <int K, int UNROLL>
-__device__ __forceinline__ void scatter_vec4(const int *__restrict__ idx, const float *__restrict__ val,
+__device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const float *__restrict__ val,
                                              const uint8_t *__restrict__ csel, float *__restrict__ gs,
                                              const float *gsm, int b, int e, int batch0, int stride)
 {
-    constexpr int LPE = K / 4;
-    constexpr int EPI = 32 / LPE;
+    using LY = Lay<K>;
+    constexpr int EPL = LY::EPL, L = LY::L, EPI = LY::EPI;
     const int lane = lane_id();
-    const int q = lane / LPE, t = lane % LPE;
+    const int q = lane / L, t = lane % L;
+    const float *gsm_q = gsm + q * L;
 
     int base = b + batch0 * 32;
     int nxt_c = 0;
@@ -77,7 +88,7 @@ __device__ __forceinline__ void scatter_vec4(const int *__restrict__ idx, const 
             nxt_w = ld_stream_f32(val + nb + lane);
         }
         for (int j = 0; j < n; j += EPI * UNROLL) {
-            uint32_t s4[UNROLL];
+            uint32_t s[UNROLL];
             float w[UNROLL];
             size_t off[UNROLL];
             bool ok[UNROLL];
@@ -87,18 +98,17 @@ __device__ __forceinline__ void scatter_vec4(const int *__restrict__ idx, const 
                 const int c = __shfl_sync(kFullB, my_c, ej & 31);
                 w[u] = __shfl_sync(kFullB, my_w, ej & 31);
                 ok[u] = ej < n;
-                off[u] = (size_t)c * K + 4 * t;
-                s4[u] = 0;
-                if (ok[u]) s4[u] = __ldg(reinterpret_cast<const uint32_t *>(csel + off[u]));
+                off[u] = (size_t)c * K + EPL * t;
+                s[u] = 0;
+                if (ok[u]) s[u] = SelLoad<EPL>::load(csel + off[u]);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 if (ok[u]) {
-                    const float x0 = w[u] * gsm[s4[u] & 0xff];
-                    const float x1 = w[u] * gsm[(s4[u] >> 8) & 0xff];
-                    const float x2 = w[u] * gsm[(s4[u] >> 16) & 0xff];
-                    const float x3 = w[u] * gsm[s4[u] >> 24];
-                    red_add_f32x4(gs + off[u], x0, x1, x2, x3);
+                    float x[EPL];
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) x[i] = w[u] * gsm_q[LY::word((s[u] >> (8 * i)) & 0xff)];
+                    SelLoad<EPL>::red(gs + off[u], x);
                 }
             }
         }
@@ -134,10 +144,7 @@ template <int K>
 __device__ __forceinline__ void scatter_row(const int *idx, const float *val, const uint8_t *csel, float *gs,
                                             const float *gsm, int k, int b, int e, int batch0, int stride)
 {
-    if constexpr (K == 8) scatter_vec4<8, 2>(idx, val, csel, gs, gsm, b, e, batch0, stride);
-    else if constexpr (K == 16) scatter_vec4<16, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
-    else if constexpr (K == 32) scatter_vec4<32, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
-    else if constexpr (K == 64) scatter_vec4<64, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
+    if constexpr (Lay<K>::kFast) scatter_fast<K, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
     else scatter_any_k(idx, val, csel, gs, gsm, k, b, e, batch0, stride);
 }
 
@@ -149,9 +156,9 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
                  const float *__restrict__ row_div, SchedWorkspace *ws, int *__restrict__ long_rows,
                  int rows_per_grab)
 {
-    __shared__ __align__(16) float smem[kBwdWarps * kAccDim];
+    extern __shared__ __align__(16) float smem[];
     const int lane = lane_id();
-    float *gsm = smem + (threadIdx.x >> 5) * kAccDim;
+    float *gsm = smem + (threadIdx.x >> 5) * Lay<K>::kWords;
     for (;;) {
         int first = 0;
         if (lane == 0) first = atomicAdd(&ws->row_counter, rows_per_grab);
@@ -173,7 +180,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
             }
             const bool has_div = row_div != nullptr;
             __syncwarp();
-            stage_row(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
+            stage_row<K>(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
             scatter_row<K>(idx, val, csel, gs, gsm, k, b, e, 0, 1);
         }
     }
@@ -186,10 +193,10 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
                       const uint8_t *__restrict__ csel, float *__restrict__ gs, int dim, int k,
                       const float *__restrict__ row_div, SchedWorkspace *ws, const int *__restrict__ long_rows)
 {
-    __shared__ __align__(16) float smem[kBwdLongWarps * kAccDim];
+    extern __shared__ __align__(16) float smem[];
     __shared__ int s_item;
     const int warp = threadIdx.x >> 5;
-    float *gsm = smem + warp * kAccDim;
+    float *gsm = smem + warp * Lay<K>::kWords;
     const int n_long = ws->long_count;
     for (;;) {
         __syncthreads();
@@ -200,7 +207,7 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
         const int r = long_rows[item];
         const int b = row_begin[r], e = row_end[r];
         const bool has_div = row_div != nullptr;
-        stage_row(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
+        stage_row<K>(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
         scatter_row<K>(idx, val, csel, gs, gsm, k, b, e, warp, kBwdLongWarps);
     }
 }
@@ -213,15 +220,17 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
                               int64_t n_edges, int dim, int k, const float *row_div, SchedWorkspace *ws,
                               cudaStream_t stream)
 {
+    const size_t smem_main = (size_t)kBwdWarps * Lay<K>::kWords * sizeof(float);
+    const size_t smem_long = (size_t)kBwdLongWarps * Lay<K>::kWords * sizeof(float);
     static bool configured = false;
     static int blocks_per_sm = 1;
     static int sms = kNumSMsB200;
     if (!configured) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sspmm_bwd_kernel<K>, kBwdThreads, 0);
+        cudaFuncSetAttribute(sspmm_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main);
+        cudaFuncSetAttribute(sspmm_bwd_long_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sspmm_bwd_kernel<K>, kBwdThreads, smem_main);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
+        sms = device_sm_count();
         configured = true;
     }
     int *long_rows = reinterpret_cast<int *>(ws + 1);
@@ -231,11 +240,11 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
     if (err != cudaSuccess) return err;
     const int grid = sms * blocks_per_sm;
     const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kBwdWarps);
-    sspmm_bwd_kernel<K><<<grid, kBwdThreads, 0, stream>>>(row_begin, row_end, idx, val, g, csel, gs, (int)n_rows, dim,
+    sspmm_bwd_kernel<K><<<grid, kBwdThreads, smem_main, stream>>>(row_begin, row_end, idx, val, g, csel, gs, (int)n_rows, dim,
                                                           k, row_div, ws, long_rows, rpg);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    sspmm_bwd_long_kernel<K><<<sms, kBwdLongThreads, 0, stream>>>(row_begin, row_end, idx, val, g, csel, gs, dim, k,
+    sspmm_bwd_long_kernel<K><<<sms, kBwdLongThreads, smem_long, stream>>>(row_begin, row_end, idx, val, g, csel, gs, dim, k,
                                                                   row_div, ws, long_rows);
     return cudaGetLastError();
 }
@@ -252,7 +261,7 @@ extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
-    if (k < 1 || k > dim) return MAXK_ERR_BAD_K;
+    if (k < 1 || k > kAccDim) return MAXK_ERR_BAD_K;
     if (n_rows < 0 || n_dst < 0 || n_edges < 0 || n_rows > INT32_MAX || n_edges > INT32_MAX) return MAXK_ERR_SIZE;
     if (n_dst == 0) return MAXK_OK;
     if (!gs) return MAXK_ERR_NULL;
@@ -260,7 +269,8 @@ extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_
         return status_from_cuda(cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream));
     if (!row_begin || !row_end || !indices || !values || !g || !cbsr_sel || !workspace) return MAXK_ERR_NULL;
     if (workspace_bytes < maxk_spgemm_workspace_bytes(n_rows)) return MAXK_ERR_WORKSPACE;
-    if (((uintptr_t)gs | (uintptr_t)g | (uintptr_t)workspace) & 15) return MAXK_ERR_ALIGN;
+    if (((uintptr_t)gs | (uintptr_t)workspace) & 15) return MAXK_ERR_ALIGN;
+    if ((uintptr_t)g & 3) return MAXK_ERR_ALIGN;
     if ((k % 4 == 0) && ((uintptr_t)cbsr_sel & 3)) return MAXK_ERR_ALIGN;
     SchedWorkspace *ws = reinterpret_cast<SchedWorkspace *>(workspace);
     cudaError_t err;

@@ -8,11 +8,14 @@
 // One warp per row, the row lives in registers (8 values per lane for dim = 256, loaded as two
 // coalesced float4).  Exact selection:
 //   1. keys  = order-preserving uint32 image of the floats (NaN largest, -0 == +0);
-//   2. T     = k-th largest key by a 32-step bitwise radix descent (warp REDUX per step);
-//   3. every key > T is selected; of the keys == T the lowest columns are taken until k
-//      (ballot-free: per-lane counts + warp exclusive scans in column order);
-//   4. entries are emitted in column order (MAXK_ORDER_COLUMN_ASC) or rank-sorted by
-//      (value desc, column asc) through shared memory (MAXK_ORDER_VALUE_DESC = torch order).
+//   2. bisection in KEY space between the row's min and max key: count(key >= mid) with one
+//      warp REDUX per step; stops as soon as a threshold with exactly k keys above it is found
+//      (about log2(256)+2 steps on continuous data, at most 33 when ties straddle rank k);
+//   3. every key > T is selected; of the keys == T the lowest columns are taken until k;
+//   4. the output position of every selected entry is computed from 8 warp ballots with
+//      popcounts only (no shuffles): column order (MAXK_ORDER_COLUMN_ASC), bank-residue-major
+//      order (MAXK_ORDER_BANKED, what the SpGEMM/SSpMM kernels are conflict-minimal on), or
+//      rank-sorted by (value desc, column asc) through shared memory (MAXK_ORDER_VALUE_DESC).
 // The same pass can write the dense masked row (the MaxK nonlinearity output), so the
 // reference's topk + zeros_like + scatter_ + multiply (4 dense passes) is one read + one write.
 #include "maxk_common.cuh"
@@ -23,24 +26,19 @@ constexpr int kTopkThreads = 256;
 constexpr int kTopkWarps = kTopkThreads / 32;
 constexpr unsigned kFullT = 0xffffffffu;
 
-__device__ __forceinline__ int warp_excl_scan(int v, int &total)
-{
-    const int lane = lane_id();
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int n = __shfl_up_sync(kFullT, inc, d);
-        if (lane >= d) inc += n;
-    }
-    total = __shfl_sync(kFullT, inc, 31);
-    return inc - v;
-}
-
 // Column owned by (lane, slot): slots 0-3 -> 4*lane+slot, slots 4-7 -> 128+4*lane+(slot-4).
 __device__ __forceinline__ int col_of(int lane, int slot) { return (slot < 4 ? 0 : 128) + 4 * lane + (slot & 3); }
 
+__device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
+{
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) c += (key[s] >= t) ? 1 : 0;
+    return __reduce_add_sync(kFullT, c);
+}
+
 __global__ void __launch_bounds__(kTopkThreads)
-topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, int order,
+topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, int order, int bank_mod,
                  float *__restrict__ out_val, uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32,
                  int64_t *__restrict__ out_i64, float *__restrict__ masked)
 {
@@ -50,6 +48,11 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
+    const unsigned lt = (1u << lane) - 1u;
+    // lanes whose columns fall in the same residue classes mod bank_mod as mine (bank_mod in {4,8,16})
+    const int groups = bank_mod >= 4 ? bank_mod / 4 : 1;
+    const int grp = lane % groups;
+    const unsigned cm = (groups == 1 ? 0xffffffffu : groups == 2 ? 0x55555555u : 0x11111111u) << grp;
 
     for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
         const float *row = x + r * dim;
@@ -67,57 +70,67 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             }
         }
         uint32_t key[8];
+        uint32_t kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) key[s] = (col_of(lane, s) < dim) ? order_key(v[s]) : 0u;  // pad: below every real key
+        for (int s = 0; s < 8; ++s) {
+            const bool real = dim == kAccDim || col_of(lane, s) < dim;
+            key[s] = real ? order_key(v[s]) : 0u;   // pad: below every real key (real keys are >= 0x007fffff)
+            kmax = max(kmax, key[s]);
+            if (real) kmin = min(kmin, key[s]);
+        }
+        kmax = __reduce_max_sync(kFullT, kmax);
+        kmin = __reduce_min_sync(kFullT, kmin);
 
-        // ---- k-th largest key: T = max{t : #(key >= t) >= k} -------------------------------
-        uint32_t T = 0;
-#pragma unroll 1
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t cand = T | (1u << bit);
-            int cnt = 0;
-#pragma unroll
-            for (int s = 0; s < 8; ++s) cnt += (key[s] >= cand) ? 1 : 0;
-            cnt = __reduce_add_sync(kFullT, cnt);
-            if (cnt >= k) T = cand;
+        // ---- threshold: lo has count(>= lo) >= k, hi (exclusive, 33 bits) has count(>= hi) < k ---
+        uint32_t T = kmin;
+        if (count_ge(key, kmax) >= k) {
+            T = kmax;                            // rank k lies inside the run of maximal keys
+        } else {
+            uint32_t lo = kmin, hi = kmax;       // count(>= kmax) < k here
+            while (hi - lo > 1u) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                const int c = count_ge(key, mid);
+                if (c >= k) lo = mid; else hi = mid;
+                if (c == k) break;               // exactly k keys at or above mid: no tie at the boundary
+            }
+            T = lo;
         }
 
-        // ---- selection flags in column order ------------------------------------------------
-        int gt_lo = 0, gt_hi = 0, eq_lo = 0, eq_hi = 0;
+        // ---- selection: key > T, plus the lowest-column keys == T until k -----------------------
+        unsigned b_gt[8], b_eq[8];
+        int gt_total = 0;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) { gt_lo += key[s] > T; eq_lo += key[s] == T; }
+        for (int s = 0; s < 8; ++s) {
+            b_gt[s] = __ballot_sync(kFullT, key[s] > T);
+            b_eq[s] = __ballot_sync(kFullT, key[s] == T);
+            gt_total += __popc(b_gt[s]);
+        }
+        const int need_eq = k - gt_total;        // >= 0; 0 only when the bisection stopped between two keys
+        // rank of my equal keys in column order: (half, lane, slot&3)
+        int eq_lo_before = 0, eq_lo_total = 0, eq_hi_before = 0;
 #pragma unroll
-        for (int s = 4; s < 8; ++s) { gt_hi += key[s] > T; eq_hi += key[s] == T; }
-        int tot_eq_lo, tot_eq_hi, tot_gt_lo, tot_gt_hi;
-        const int eq_before_lo = warp_excl_scan(eq_lo, tot_eq_lo);
-        const int eq_before_hi = warp_excl_scan(eq_hi, tot_eq_hi) + tot_eq_lo;
-        (void)tot_eq_hi;
-        const int gt_total = __reduce_add_sync(kFullT, gt_lo + gt_hi);
-        const int need_eq = k - gt_total;  // >= 1 by construction of T
-
+        for (int u = 0; u < 4; ++u) {
+            eq_lo_before += __popc(b_eq[u] & lt);
+            eq_lo_total += __popc(b_eq[u]);
+            eq_hi_before += __popc(b_eq[u + 4] & lt);
+        }
         bool selb[8];
-        int sel_lo = 0, sel_hi = 0;
         {
-            int eq_rank = eq_before_lo;
+            int rk = eq_lo_before;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const bool is_eq = key[s] == T;
-                selb[s] = (key[s] > T) || (is_eq && eq_rank < need_eq);
-                eq_rank += is_eq;
-                sel_lo += selb[s];
+                selb[s] = (key[s] > T) || (is_eq && rk < need_eq);
+                rk += is_eq;
             }
-            eq_rank = eq_before_hi;
+            rk = eq_lo_total + eq_hi_before;
 #pragma unroll
             for (int s = 4; s < 8; ++s) {
                 const bool is_eq = key[s] == T;
-                selb[s] = (key[s] > T) || (is_eq && eq_rank < need_eq);
-                eq_rank += is_eq;
-                sel_hi += selb[s];
+                selb[s] = (key[s] > T) || (is_eq && rk < need_eq);
+                rk += is_eq;
             }
         }
-        const int pos_lo = warp_excl_scan(sel_lo, tot_gt_lo);            // tot_gt_lo = #selected in low half
-        const int pos_hi = warp_excl_scan(sel_hi, tot_gt_hi) + tot_gt_lo;
-        (void)tot_gt_hi;
 
         if (masked != nullptr) {
             float *mrow = masked + r * dim;
@@ -135,23 +148,60 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             }
         }
 
-        // ---- compact the k selected entries (column order) into shared memory -----------------
-        {
-            int p = pos_lo;
+        // ---- output positions from the selection ballots ---------------------------------------
+        unsigned bs[8];
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (selb[s]) { s_val[warp][p] = v[s]; s_key[warp][p] = key[s]; s_col[warp][p] = (uint8_t)col_of(lane, s); ++p; }
-            p = pos_hi;
+        for (int s = 0; s < 8; ++s) bs[s] = __ballot_sync(kFullT, selb[s]);
+        int pos[8];
+        if (order == MAXK_ORDER_BANKED && bank_mod >= 4) {
+            // class of (lane, slot) = 4*grp + (slot&3); classes ascending, columns ascending inside
+            int my_cnt = 0;
 #pragma unroll
-            for (int s = 4; s < 8; ++s)
-                if (selb[s]) { s_val[warp][p] = v[s]; s_key[warp][p] = key[s]; s_col[warp][p] = (uint8_t)col_of(lane, s); ++p; }
+            for (int s = 0; s < 8; ++s) my_cnt += selb[s] ? 1 : 0;
+            const int grp_total = __reduce_add_sync(cm, my_cnt);     // selected entries of my lane group
+            int base = 0;
+            for (int g = 0; g < groups - 1; ++g) {
+                const int tg = __shfl_sync(kFullT, grp_total, g);    // lane g belongs to group g
+                if (g < grp) base += tg;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c_lo = __popc(bs[u] & cm), c_hi = __popc(bs[u + 4] & cm);
+                pos[u] = base + __popc(bs[u] & cm & lt);
+                pos[u + 4] = base + c_lo + __popc(bs[u + 4] & cm & lt);
+                base += c_lo + c_hi;
+            }
+        } else {
+            // column order: (half, lane, slot&3)
+            int lo_before = 0, lo_total = 0, hi_before = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                lo_before += __popc(bs[u] & lt);
+                lo_total += __popc(bs[u]);
+                hi_before += __popc(bs[u + 4] & lt);
+            }
+            int p = lo_before;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { pos[s] = p; p += selb[s] ? 1 : 0; }
+            p = lo_total + hi_before;
+#pragma unroll
+            for (int s = 4; s < 8; ++s) { pos[s] = p; p += selb[s] ? 1 : 0; }
         }
+
+        // ---- stage the k entries in shared memory, then coalesced stores -----------------------
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (selb[s]) {
+                s_val[warp][pos[s]] = v[s];
+                s_key[warp][pos[s]] = key[s];
+                s_col[warp][pos[s]] = (uint8_t)col_of(lane, s);
+            }
         __syncwarp();
 
         for (int i = lane; i < k; i += 32) {
             int dst = i;
             if (order == MAXK_ORDER_VALUE_DESC) {
-                // rank sort: entries are in column order, so "earlier index" == "lower column"
+                // rank sort: entries are staged in column order, so "earlier index" == "lower column"
                 const uint32_t ki = s_key[warp][i];
                 int rank = 0;
                 for (int j = 0; j < k; ++j) {
@@ -274,6 +324,8 @@ static int grid_for_rows(int64_t n_rows)
 
 using namespace maxk;
 
+extern "C" int maxk_banked_modulus(int k) { return banked_modulus(k); }
+
 extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order, float *cbsr_val,
                               uint8_t *cbsr_sel, int32_t *idx_i32, int64_t *idx_i64, float *masked,
                               maxk_stream_t stream)
@@ -284,8 +336,10 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     if (n_rows == 0) return MAXK_OK;
     if (!x || !cbsr_val) return MAXK_ERR_NULL;
     if (dim == kAccDim && (((uintptr_t)x | (uintptr_t)masked) & 15)) return MAXK_ERR_ALIGN;
+    if (order != MAXK_ORDER_VALUE_DESC && order != MAXK_ORDER_COLUMN_ASC && order != MAXK_ORDER_BANKED)
+        return MAXK_ERR_SIZE;
     topk_cbsr_kernel<<<grid_for_rows(n_rows), kTopkThreads, 0, (cudaStream_t)stream>>>(
-        x, n_rows, dim, k, order, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked);
+        x, n_rows, dim, k, order, banked_modulus(k), cbsr_val, cbsr_sel, idx_i32, idx_i64, masked);
     return status_from_cuda(cudaGetLastError());
 }
 

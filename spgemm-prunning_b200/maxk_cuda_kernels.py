@@ -27,6 +27,7 @@ WARP_MAX_NZ = 64        # kernels/generate_meta.py:9
 
 ORDER_VALUE_DESC = 0
 ORDER_COLUMN_ASC = 1
+ORDER_BANKED = 2          # (column mod banked_modulus(k), column): fewest bank conflicts in fwd/bwd
 
 _c_i64 = ctypes.c_int64
 _c_int = ctypes.c_int
@@ -37,6 +38,7 @@ _c_size = ctypes.c_size_t
 _SIGNATURES = {
     "maxk_abi_version": (_c_int, []),
     "maxk_status_string": (ctypes.c_char_p, [_c_int]),
+    "maxk_banked_modulus": (_c_int, [_c_int]),
     "maxk_topk_cbsr": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
     "maxk_spgemm_forward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_int,
                                      _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
@@ -191,7 +193,7 @@ def sspmm_backward_csr(row_begin, row_end, indices, values, grad_output, cbsr_se
     return out
 
 
-def topk_cbsr(x, k, order=ORDER_COLUMN_ASC, want_sel=True, want_i32=False, want_i64=False, want_masked=False):
+def topk_cbsr(x, k, order=ORDER_BANKED, want_sel=True, want_i32=False, want_i64=False, want_masked=False):
     """Exact row-wise top-k of x[N, D<=256] -> dict(values, sel, i32, i64, masked)."""
     x = _cuda(x, "input", torch.float32)
     _check(x.dim() == 2, "Input must be 2D tensor")

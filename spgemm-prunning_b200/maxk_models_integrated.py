@@ -33,7 +33,7 @@ class MaxK(Function):
     @staticmethod
     def forward(ctx, input, k=1):
         _require_cuda_2d(input, "MaxK")
-        r = _k.topk_cbsr(input, int(k), order=_k.ORDER_COLUMN_ASC, want_masked=True)
+        r = _k.topk_cbsr(input, int(k), order=_k.ORDER_BANKED, want_masked=True)
         ctx.save_for_backward(r["sel"])
         return r["masked"]
 
@@ -47,7 +47,7 @@ class OPTMaxK(Function):
     """MaxK activation that also returns the CBSR pair (model_integrated_v3.py:28-43).
 
     topk_indices is int64 like torch.topk's (it may be fed to scatter_/gather by callers); the
-    entries of a row are in column order, not value order -- every consumer on this path
+    entries of a row are in bank-residue-major column order, not value order -- every consumer on this path
     (spmm, scatter) is order-independent.
 
     reference_compat: the reference's backward returns grad_output * mask only and DROPS
@@ -61,7 +61,7 @@ class OPTMaxK(Function):
     @staticmethod
     def forward(ctx, input, k=1):
         _require_cuda_2d(input, "OPTMaxK")
-        r = _k.topk_cbsr(input, int(k), order=_k.ORDER_COLUMN_ASC, want_masked=True, want_i64=True)
+        r = _k.topk_cbsr(input, int(k), order=_k.ORDER_BANKED, want_masked=True, want_i64=True)
         ctx.save_for_backward(r["sel"])
         ctx.mark_non_differentiable(r["i64"])
         return r["masked"], r["values"], r["i64"]

@@ -39,7 +39,7 @@ class MaxKSpGEMMFunction(Function):
         n, d = input_features.shape
         k_value = int(k_value)
         if k_value < d:                                        # maxk_spgemm_function.py:51-57
-            r = maxk_cuda_kernels.topk_cbsr(input_features, k_value, order=maxk_cuda_kernels.ORDER_COLUMN_ASC)
+            r = maxk_cuda_kernels.topk_cbsr(input_features, k_value, order=maxk_cuda_kernels.ORDER_BANKED)
             sparse_data, sparse_selector = r["values"], r["sel"]
         else:                                                  # :58-63, k >= D keeps every feature
             if d > maxk_cuda_kernels.FULL_DIM:

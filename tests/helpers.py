@@ -8,12 +8,12 @@ from synth_graphs import synth_graph
 RTOL, ATOL = 1e-5, 1e-6     # north star tolerance for fp32 outputs vs the fp64 oracle
 
 
-def make_problem(n, e, k, dim=256, kind="uniform", seed=0, values="uniform", signed=False):
+def make_problem(n, e, k, dim=256, kind="uniform", seed=0, values="uniform", signed=False, order=2):
     g = synth_graph(n, e, seed=seed + 123, kind=kind, values=values)
     gen = torch.Generator().manual_seed(seed)
     x = torch.randn(n, dim, generator=gen) if signed else torch.rand(n, dim, generator=gen)
     grad = torch.rand(n, dim, generator=gen)
-    vals, cols = oracle.topk(x.numpy(), k, order=1)
+    vals, cols = oracle.topk(x.numpy(), k, order=order)
     return {"graph": g, "x": x, "grad": grad, "k": k, "dim": dim,
             "cbsr_val": vals, "cbsr_col": cols, "cbsr_sel": cols.astype(np.uint8)}
 

@@ -25,7 +25,7 @@ def kern():
 def test_topk_exact(kern, k, signed):
     gen = torch.Generator().manual_seed(k)
     x = torch.randn(517, 256, generator=gen) if signed else torch.rand(517, 256, generator=gen)
-    for order in (0, 1):
+    for order in (0, 1, 2):
         ev, ec = oracle.topk(x.numpy(), k, order)
         r = kern.topk_cbsr(x.cuda(), k, order=order, want_i32=True, want_i64=True, want_masked=True)
         assert np.array_equal(r["sel"].cpu().numpy(), ec.astype(np.uint8))
@@ -46,8 +46,8 @@ def test_topk_ties_lowest_column(kern):
         [float("inf") if i % 50 == 0 else -float("inf") for i in range(256)],
     ]
     x = torch.tensor(rows, dtype=torch.float32)
-    for k in (1, 2, 5, 32, 33, 128, 255):
-        for order in (0, 1):
+    for k in (1, 2, 5, 8, 16, 32, 33, 64, 128, 255):
+        for order in (0, 1, 2):
             ev, ec = oracle.topk(x.numpy(), k, order)
             r = kern.topk_cbsr(x.cuda(), k, order=order)
             assert np.array_equal(r["sel"].cpu().numpy(), ec.astype(np.uint8)), (k, order)
@@ -85,8 +85,9 @@ CASES = [
 
 @pytest.mark.parametrize("n,e,kind", CASES)
 @pytest.mark.parametrize("k", [8, 16, 32, 64, 19, 3])
-def test_forward_backward_vs_oracle(kern, n, e, kind, k):
-    p = make_problem(n, e, k, kind=kind, seed=k, signed=True)
+@pytest.mark.parametrize("order", [2, 0])     # kernels must be correct for ANY entry order, fastest on 2
+def test_forward_backward_vs_oracle(kern, n, e, kind, k, order):
+    p = make_problem(n, e, k, kind=kind, seed=k, signed=True, order=order)
     ip, ix, va = graph_np(p["graph"])
     cip, cix, cva = graph_cuda(p["graph"])
     data, sel = torch.from_numpy(p["cbsr_val"]).cuda(), torch.from_numpy(p["cbsr_sel"]).cuda()

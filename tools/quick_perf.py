@@ -49,19 +49,23 @@ def main():
     w4, nw = K.build_warp4(ip, 64)
     print("graph %s n=%d e=%d W=%d maxdeg=%d" % (a.shape, n, e, nw, int((ip[1:] - ip[:-1]).max())))
     for k in [int(s) for s in a.ks.split(",")]:
-        r = K.topk_cbsr(x, k, order=1)
+        r = K.topk_cbsr(x, k, order=2)
         data, sel = r["values"], r["sel"]
-        t_topk = timeit(lambda: K.topk_cbsr(x, k, order=1))
+        r0 = K.topk_cbsr(x, k, order=0)
+        t_topk = timeit(lambda: K.topk_cbsr(x, k, order=2))
         t_topk0 = timeit(lambda: K.topk_cbsr(x, k, order=0))
         t_torch = timeit(lambda: torch.topk(x, k, dim=1))
         t_fwd = timeit(lambda: K.spgemm_forward_csr(ip[:-1], ip[1:], ix, va, data, sel))
         t_bwd = timeit(lambda: K.sspmm_backward_csr(ip[:-1], ip[1:], ix, va, grad, sel))
+        t_fwd0 = timeit(lambda: K.spgemm_forward_csr(ip[:-1], ip[1:], ix, va, r0["values"], r0["sel"]))
+        t_bwd0 = timeit(lambda: K.sspmm_backward_csr(ip[:-1], ip[1:], ix, va, grad, r0["sel"]))
         bt = n * 256 * 4 + n * k * 5
         bf = (n + 1) * 4 + e * 8 + n * k * 5 + n * 256 * 4
         bb = (n + 1) * 4 + e * 8 + n * 256 * 4 + n * k * 5
         line = "k=%d topk %.3f ms (%.0f GB/s; sorted %.3f; torch %.3f) | fwd %.3f ms (%.0f GB/s alg, gather %.0f GB/s) | bwd %.3f ms (%.0f GB/s alg)" % (
             k, t_topk[0], bt / t_topk[0] / 1e6, t_topk0[0], t_torch[0], t_fwd[0], bf / t_fwd[0] / 1e6,
             e * k * 5 / t_fwd[0] / 1e6, t_bwd[0], bb / t_bwd[0] / 1e6)
+        line += " | value-order CBSR: fwd %.3f bwd %.3f" % (t_fwd0[0], t_bwd0[0])
         if a.ref and oracle.ref_cuda_available():
             t_rf = timeit(lambda: oracle.ref_cuda_forward(w4, ix, va, data, sel, nw), warm=2, reps=3)
             t_rb = timeit(lambda: oracle.ref_cuda_backward(w4, ix, va, grad, sel, nw), warm=2, reps=3)
