@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library loads and exports every symbol include/maxk_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "maxk_b200.h")
+LIB = os.path.join(ROOT, "spgemm-prunning_b200", "lib", "libmaxk_b200.so")
+
+
+def declared_functions():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(maxk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_three_hot_path_operations():
+    names = declared_functions()
+    for required in ("maxk_topk_cbsr", "maxk_spgemm_forward", "maxk_sspmm_backward", "maxk_warp4_scan",
+                     "maxk_warp4_fill", "maxk_warp4_to_rows"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "build first: python __graft_entry__.py"
+    lib = ctypes.CDLL(LIB)
+    for name in declared_functions():
+        assert hasattr(lib, name), "libmaxk_b200.so does not export " + name
+
+
+def test_python_binding_binds_exactly_the_header():
+    import maxk_cuda_kernels as k
+    assert sorted(k._SIGNATURES) == declared_functions()
+    assert k._lib.maxk_abi_version() == 1
+    assert k._lib.maxk_status_string(-2).decode().startswith("dim must")
+    assert [k._lib.maxk_banked_modulus(x) for x in (8, 16, 32, 64, 19)] == [4, 4, 8, 16, 1]
+    assert k._lib.maxk_spgemm_workspace_bytes(1000) >= 4000
+
+
+def test_reference_export_names_are_present():
+    """Python-visible surface of the reference extension (cuda_kernel_bindings.cpp:429-490, binding_v2.py:488-561)."""
+    import maxk_cuda_kernels as k
+    for name in ("spmm_maxk_forward", "spmm_maxk_backward", "cuda_topk_maxk", "cuda_topk_maxk_float",
+                 "prepare_cbsr_format_maxk", "load_warp4_metadata", "load_warp4_metadata_csc", "cusparse_spmm",
+                 "generate_sparse_selector", "benchmark_spmm_maxk", "validate_spmm_maxk",
+                 "validate_spmm_maxk_backward", "CudaTimer"):
+        assert hasattr(k, name), name
+
+
+def test_product_code_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under spgemm-prunning_b200/ may import or load it."""
+    pkg = os.path.join(ROOT, "spgemm-prunning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "libmaxk_oracle" not in text and "libmaxk_ref" not in text, f

@@ -1,0 +1,78 @@
+"""CPU: host-side pieces of the operator surface (loaders, synthetic graphs, argument checking)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from graph_loader import GraphDataLoader, save_warp4, warp4_path
+from synth_graphs import SHAPES, shape_graph, symmetrize, synth_graph
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_graph_loader_round_trip_and_reference_edge_values(tmp_path):
+    ref = np.load(os.path.join(GOLD, "ref_py.npz"))
+    loader = GraphDataLoader(str(tmp_path) + "/")
+    loader.save_graph("small", ref["indptr"], ref["indices"])
+    assert loader.get_available_graphs() == ["small"]
+    g = loader.load_graph("small.dgl")                      # extension is stripped like graph_loader.py:52
+    assert np.array_equal(g["indptr"], ref["indptr"]) and np.array_equal(g["indices"], ref["indices"])
+    assert g["v_num"] == 200 and g["e_num"] == 3000
+    assert np.array_equal(g["values"], ref["loader_values"])   # np.random.seed(123) U[0,1), graph_loader.py:71-72
+    with pytest.raises(FileNotFoundError):
+        loader.load_graph("missing")
+
+
+def test_warp4_file_convention(tmp_path):
+    p = warp4_path("reddit.dgl", root=str(tmp_path))
+    assert p.endswith("w12_nz64_warp_4/reddit.dgl.warp4")
+    assert warp4_path("g", csc=True).endswith("w12_nz64_warp_4_csc/g.warp4_csc")
+    quads, _ = oracle.warp4(np.array([0, 3, 3, 200], np.int32), 64)
+    save_warp4(p, quads)
+    assert np.array_equal(np.fromfile(p, dtype=np.int32), quads)
+    assert quads.reshape(-1, 4).tolist() == [[0, 0, 3, 0], [2, 3, 64, 0], [2, 67, 64, 0], [2, 131, 64, 0], [2, 195, 5, 0]]
+
+
+@pytest.mark.parametrize("kind", ["uniform", "powerlaw"])
+def test_synthetic_graph_is_valid_csr(kind):
+    g = synth_graph(1000, 25000, seed=1, kind=kind)
+    ip, ix = g["indptr"].numpy(), g["indices"].numpy()
+    assert ip[0] == 0 and ip[-1] == 25000 == ix.size and (np.diff(ip) >= 0).all()
+    assert ix.min() >= 0 and ix.max() < 1000
+    for r in (0, 10, 999):
+        assert (np.diff(ix[ip[r]:ip[r + 1]]) >= 0).all()          # sorted within a row
+    g2 = synth_graph(1000, 25000, seed=1, kind=kind)
+    assert torch.equal(g["indices"], g2["indices"]) and torch.equal(g["values"], g2["values"])   # seeded
+    if kind == "powerlaw":
+        assert np.diff(ip).max() > 5 * 25           # heavy tail: hubs well above the mean degree
+
+
+def test_symmetrize_is_symmetric_with_self_loops():
+    s = symmetrize(synth_graph(200, 1500, seed=4))
+    import scipy.sparse as sp
+    a = sp.csr_matrix((s["values"].numpy(), s["indices"].numpy(), s["indptr"].numpy()), shape=(200, 200))
+    assert (a != a.T).nnz == 0 and (a.diagonal() == 1).all()
+
+
+def test_named_shapes_match_baseline_configs():
+    assert SHAPES["reddit"] == (232_965, 114_615_892) and SHAPES["flickr"][0] == 89_250
+    g = shape_graph("flickr", scale=0.01)
+    assert g["v_num"] == 892 and abs(g["e_num"] / g["v_num"] - SHAPES["flickr"][1] / SHAPES["flickr"][0]) < 1
+
+
+def test_ops_refuse_cpu_tensors():
+    """No CPU fallback: the binding raises before reaching the library when a tensor is not on a GPU."""
+    import maxk_cuda_kernels as k
+    from maxk_models_integrated import MaxK
+    from maxk_spgemm_function import maxk_spgemm
+    x = torch.rand(4, 256)
+    with pytest.raises(RuntimeError):
+        k.topk_cbsr(x, 8)
+    with pytest.raises(RuntimeError):
+        MaxK.apply(x, 8)
+    with pytest.raises(RuntimeError):
+        maxk_spgemm(torch.zeros(1, dtype=torch.int32), torch.ones(1), x, 8, None, 0, torch.zeros(5, dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        k.load_warp4_metadata("definitely_missing_graph")

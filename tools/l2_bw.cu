@@ -47,6 +47,19 @@ __global__ void gather(const float* __restrict__ vals, const unsigned char* __re
   }
   if(acc==12345.f) out[0]=acc;
 }
+// RED test: each warp adds 128-byte rows (8 lanes x red.v4) to random rows, 4 rows per instruction
+__global__ void redtest(float* __restrict__ dst, const int* __restrict__ idx, size_t nidx, int vec){
+  size_t warp = (blockIdx.x*(size_t)blockDim.x+threadIdx.x)>>5, nwarps=((size_t)gridDim.x*blockDim.x)>>5; int lane=threadIdx.x&31;
+  const int q=lane>>3, t=lane&7;
+  for(size_t i=warp*16;i+16<=nidx;i+=nwarps*16){
+    #pragma unroll
+    for(int u=0;u<4;++u){
+      if(vec){ int c=__ldg(idx+i+u*4+q); float* p=dst+(size_t)c*32+4*t;
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(1.f),"f"(1.f),"f"(1.f),"f"(1.f) : "memory"); }
+      else { for(int v=0;v<4;++v){ int c=__ldg(idx+i+u*4+v); atomicAdd(dst+(size_t)c*32+lane, 1.f);} }
+    }
+  }
+}
 template<int MODE,int U>
 void run_gather(const char* name, float* vals, unsigned char* sel, int* idx, size_t nidx, size_t nrows, int ws, float* out, int ctas, int threads){
   cudaEvent_t a,b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -83,6 +96,13 @@ int main(){
     run_gather<1,2>("8lanes16B 4rows/instr", vals,sel,idx,nidx,nrows,1,out,8,256);
     run_gather<1,8>("8lanes16B 4rows/instr", vals,sel,idx,nidx,nrows,1,out,4,256);
     run_gather<2,4>("packed160B 3rows/instr", vals,sel,idx,nidx,nrows,1,out,8,256);
+    for(int vec=0; vec<2; ++vec){
+      cudaEvent_t a2,b2; cudaEventCreate(&a2); cudaEventCreate(&b2);
+      redtest<<<148*8,256>>>(vals,idx,nidx,vec); cudaDeviceSynchronize();
+      cudaEventRecord(a2); redtest<<<148*8,256>>>(vals,idx,nidx,vec); cudaEventRecord(b2); cudaEventSynchronize(b2);
+      float ms; cudaEventElapsedTime(&ms,a2,b2);
+      printf("RED 128B rows=%zu vec4=%d: %.3f ms, %.1f G rows/s, %.1f GB/s\n", nrows, vec, ms, nidx/ms/1e6, nidx*128.0/ms/1e6);
+    }
     cudaFree(vals); cudaFree(sel); cudaFree(idx);
   }
   return 0;
