@@ -1,0 +1,186 @@
+"""1-D row-sharded MaxK aggregation over the GPUs of one box (no reference counterpart --
+the reference is single-GPU, all_train.py:224).
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank p owns the rows
+[p*m, (p+1)*m) of the adjacency (m = ceil(N / P); the last rank's slab is zero-padded so every
+collective has uniform counts), the same rows of the features and of the output.
+
+forward   : local top-k -> CBSR slab [m, k]  --all_gather-->  CBSR of all N nodes
+            -> local SpGEMM over the rank's rows (global column ids)          -> out [m, 256]
+            5k bytes per node travel instead of 1 KiB (the point of the CBSR format).
+backward  : "reduce_scatter" (default): every rank scatters the outer products of ITS rows into a
+            full-size partial gs[N, k] (selectors of all nodes are resident since forward), then
+            reduce_scatter(sum) -> gs [m, k].      N*k*4 bytes per rank on the wire.
+            "allgather" (the variant BASELINE.json names): all_gather the dense gradient rows
+            [m, 256] -> [N, 256], then SSpMM over the rank's COLUMN slice A[:, rows_p]; no reduction,
+            bit-reproducible, but 256/k times more bytes on the wire.
+
+The collectives and the partition logic are backend-agnostic (the CPU tests run them on gloo with
+world_size 2); the compute backend defaults to the CUDA kernels and there is no CPU fallback in the
+product: `compute=` exists so that tests can inject the oracle.
+"""
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------------
+# partition helpers (pure tensor logic, device agnostic)
+# ------------------------------------------------------------------------------------------------
+def slab_rows(n, world):
+    """Rows per rank (uniform, last slab padded)."""
+    return (n + world - 1) // world
+
+
+def row_bounds(n, world, rank):
+    m = slab_rows(n, world)
+    lo = min(rank * m, n)
+    return lo, min(lo + m, n)
+
+
+def shard_rows(graph, world, rank):
+    """Row slab of a CSR graph: local indptr (rebased, padded to m rows), global column ids."""
+    n = graph["v_num"]
+    m = slab_rows(n, world)
+    lo, hi = row_bounds(n, world, rank)
+    indptr = graph["indptr"]
+    e0, e1 = int(indptr[lo]), int(indptr[hi])
+    local_ptr = torch.full((m + 1,), e1 - e0, dtype=torch.int32, device=indptr.device)
+    local_ptr[: hi - lo + 1] = indptr[lo:hi + 1] - e0
+    return {"indptr": local_ptr, "indices": graph["indices"][e0:e1].contiguous(),
+            "values": graph["values"][e0:e1].contiguous(), "v_num": m, "e_num": e1 - e0,
+            "n_global": n, "row_lo": lo, "row_hi": hi}
+
+
+def shard_columns(graph, world, rank):
+    """Column slab A[:, rows_p] as a CSR over ALL n source rows (padded to P*m), local column ids.
+    Used by the all_gather backward variant."""
+    n = graph["v_num"]
+    m = slab_rows(n, world)
+    lo, hi = row_bounds(n, world, rank)
+    indptr, indices, values = graph["indptr"].long(), graph["indices"], graph["values"]
+    keep = (indices >= lo) & (indices < hi)
+    rows = torch.repeat_interleave(torch.arange(n, device=indices.device), indptr[1:] - indptr[:-1])
+    counts = torch.bincount(rows[keep], minlength=n)
+    ptr = torch.zeros(world * m + 1, dtype=torch.int64, device=indices.device)
+    ptr[1:n + 1] = torch.cumsum(counts, 0)
+    ptr[n + 1:] = ptr[n]
+    return {"indptr": ptr.to(torch.int32), "indices": (indices[keep] - lo).to(torch.int32).contiguous(),
+            "values": values[keep].contiguous(), "v_num": world * m, "e_num": int(keep.sum())}
+
+
+# ------------------------------------------------------------------------------------------------
+# collectives with uniform counts
+# ------------------------------------------------------------------------------------------------
+def _all_gather(local, group):
+    world = dist.get_world_size(group)
+    out = local.new_empty((world * local.size(0),) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_sum(full, group):
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    m = full.size(0) // world
+    out = full.new_empty((m,) + tuple(full.shape[1:]))
+    if dist.get_backend(group) == "gloo":       # gloo has no reduce_scatter; only the CPU tests come here
+        dist.all_reduce(full, group=group)
+        out.copy_(full[rank * m:(rank + 1) * m])
+    else:
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# compute backend: the CUDA kernels
+# ------------------------------------------------------------------------------------------------
+class CudaCompute:
+    """The product backend: libmaxk_b200.so through maxk_cuda_kernels (raises if it is missing)."""
+
+    def __init__(self):
+        import maxk_cuda_kernels
+        self.k = maxk_cuda_kernels
+
+    def topk(self, x, k):
+        r = self.k.topk_cbsr(x, k, order=self.k.ORDER_BANKED)
+        return r["values"], r["sel"]
+
+    def spgemm(self, g, vals, sel, row_div=None):
+        ip = g["indptr"]
+        return self.k.spgemm_forward_csr(ip[:-1], ip[1:], g["indices"], g["values"], vals, sel, row_div=row_div)
+
+    def sspmm(self, g, grad, sel, row_div=None):
+        ip = g["indptr"]
+        return self.k.sspmm_backward_csr(ip[:-1], ip[1:], g["indices"], g["values"], grad, sel, row_div=row_div)
+
+
+class ShardedMaxKAggregation:
+    """top-k -> all_gather(CBSR) -> SpGEMM, and its backward, for one rank's row slab."""
+
+    def __init__(self, graph, k, group=None, backward_mode="reduce_scatter", compute=None, row_div=None):
+        if backward_mode not in ("reduce_scatter", "allgather"):
+            raise ValueError("backward_mode must be 'reduce_scatter' or 'allgather'")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.k = int(k)
+        self.n = graph["v_num"]
+        self.m = slab_rows(self.n, self.world)
+        self.rows = shard_rows(graph, self.world, self.rank)
+        self.cols = shard_columns(graph, self.world, self.rank) if backward_mode == "allgather" else None
+        self.backward_mode = backward_mode
+        self.compute = compute if compute is not None else CudaCompute()
+        self.row_div = None
+        if row_div is not None:                       # per-row divisor of the full graph -> local slab (pad with 1)
+            lo, hi = self.rows["row_lo"], self.rows["row_hi"]
+            self.row_div = torch.ones(self.m, dtype=torch.float32, device=row_div.device)
+            self.row_div[: hi - lo] = row_div[lo:hi]
+        self.sel_full = None
+
+    # x_local: [m, 256] (rows past the end of the graph are padding and may hold anything finite)
+    def forward(self, x_local):
+        vals, sel = self.compute.topk(x_local, self.k)
+        vals_full = _all_gather(vals, self.group)
+        self.sel_full = _all_gather(sel, self.group)
+        return self.compute.spgemm(self.rows, vals_full, self.sel_full, self.row_div)
+
+    def backward(self, grad_local):
+        if self.sel_full is None:
+            raise RuntimeError("backward() before forward()")
+        if self.backward_mode == "reduce_scatter":
+            partial = self.compute.sspmm(self.rows, grad_local, self.sel_full, self.row_div)   # [P*m, k]
+            return _reduce_scatter_sum(partial, self.group)
+        grad = grad_local if self.row_div is None else grad_local / self.row_div.unsqueeze(-1)
+        grad_full = _all_gather(grad, self.group)                                             # [P*m, 256]
+        lo = self.rank * self.m
+        return self.compute.sspmm(self.cols, grad_full, self.sel_full[lo:lo + self.m].contiguous())
+
+    def wire_bytes(self):
+        """Bytes each rank RECEIVES per forward / backward (for the report)."""
+        others = (self.world - 1) * self.m
+        fwd = others * self.k * 5
+        bwd = others * self.k * 4 if self.backward_mode == "reduce_scatter" else others * 256 * 4
+        return {"forward": fwd, "backward": bwd}
+
+
+class _ShardedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, layer):
+        ctx.layer = layer
+        return layer.forward(x_local)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        layer = ctx.layer
+        gs = layer.backward(grad_out.contiguous())
+        lo = layer.rank * layer.m
+        sel_local = layer.sel_full[lo:lo + layer.m].contiguous()
+        if isinstance(layer.compute, CudaCompute):
+            dense = layer.compute.k.cbsr_scatter(gs, sel_local, dim=256)
+        else:
+            dense = torch.zeros(gs.size(0), 256, dtype=gs.dtype, device=gs.device).scatter_(1, sel_local.long(), gs)
+        return dense, None
+
+
+def sharded_maxk_spgemm(x_local, layer):
+    """Autograd entry point: out_local = A[rows_p, :] @ maxk(x) with gradients flowing to x_local."""
+    return _ShardedFn.apply(x_local, layer)

@@ -69,7 +69,8 @@ def test_topk_matches_torch_topk_on_tie_free_rows(kern):
     x = torch.rand(2000, 256, generator=torch.Generator().manual_seed(7)).cuda()
     v, i = kern.cuda_topk_maxk_float(x, 32)
     tv, ti = torch.topk(x, 32, dim=1)
-    assert torch.equal(v, tv) and torch.equal(i.long(), ti)
+    tie_free = (tv[:, 1:] != tv[:, :-1]).all(dim=1)
+    assert torch.equal(v, tv) and torch.equal(i.long()[tie_free], ti[tie_free]) and tie_free.float().mean() > 0.9
     assert i.dtype == torch.int32
 
 

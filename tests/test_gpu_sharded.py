@@ -1,0 +1,89 @@
+"""GPU: the row-sharded layer on the CUDA backend over NCCL (world 1 always; world 2 when two GPUs are visible)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from helpers import assert_close
+from sharded import ShardedMaxKAggregation, sharded_maxk_spgemm, slab_rows
+from synth_graphs import synth_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem(n=3001, e=150000, k=32):
+    g = synth_graph(n, e, seed=21, kind="powerlaw")
+    gen = torch.Generator().manual_seed(5)
+    x, grad = torch.randn(n, 256, generator=gen), torch.rand(n, 256, generator=gen)
+    deg = torch.clamp((g["indptr"][1:] - g["indptr"][:-1]).float(), min=1)
+    return g, x, grad, deg, k
+
+
+def _expected(g, x, grad, deg, k):
+    ip, ix, va = (g[t].numpy() for t in ("indptr", "indices", "values"))
+    vals, cols = oracle.topk(x.numpy(), k, 2)
+    sel = cols.astype(np.uint8)
+    out = oracle.spgemm_fwd(ip, ix, va, vals, sel, deg=deg.numpy())
+    gs = oracle.sspmm_bwd(ip, ix, va, grad.numpy(), sel, deg=deg.numpy())
+    return out, gs, oracle.scatter_dense(gs, cols)
+
+
+def _run_rank(rank, world, port, mode, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g, x, grad, deg, k = _problem()
+        gc = {key: (v.cuda() if isinstance(v, torch.Tensor) else v) for key, v in g.items()}
+        n, m = g["v_num"], slab_rows(g["v_num"], world)
+        layer = ShardedMaxKAggregation(gc, k, backward_mode=mode, row_div=deg.cuda())   # default compute = CUDA kernels
+        lo = rank * m
+        rows = max(0, min(n, lo + m) - lo)
+        x_local, g_local = torch.zeros(m, 256, device="cuda"), torch.zeros(m, 256, device="cuda")
+        x_local[:rows], g_local[:rows] = x[lo:lo + rows].cuda(), grad[lo:lo + rows].cuda()
+        xl = x_local.clone().requires_grad_(True)
+        out = sharded_maxk_spgemm(xl, layer)
+        out.backward(g_local)
+        gs = layer.backward(g_local)
+        torch.cuda.synchronize()
+        np.savez(os.path.join(result_dir, "rank%d.npz" % rank), out=out.detach().cpu().numpy(), gs=gs.cpu().numpy(),
+                 xgrad=xl.grad.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _check(tmp_path, world):
+    g, x, grad, deg, k = _problem()
+    exp_out, exp_gs, exp_xgrad = _expected(g, x, grad, deg, k)
+    n, m = g["v_num"], slab_rows(g["v_num"], world)
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        lo, hi = rank * m, min(n, rank * m + m)
+        assert_close(r["out"][: hi - lo], exp_out[lo:hi], "rank %d forward" % rank)
+        assert_close(r["gs"][: hi - lo], exp_gs[lo:hi], "rank %d backward" % rank, rtol=2e-5)
+        assert_close(r["xgrad"][: hi - lo], exp_xgrad[lo:hi], "rank %d autograd" % rank, rtol=2e-5)
+
+
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather"])
+def test_world1_nccl(tmp_path, mode):
+    mp.spawn(_run_rank, args=(1, _free_port(), mode, str(tmp_path)), nprocs=1, join=True)
+    _check(tmp_path, 1)
+
+
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather"])
+def test_world2_nccl(tmp_path, mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    mp.spawn(_run_rank, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
+    _check(tmp_path, 2)

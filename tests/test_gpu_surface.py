@@ -1,0 +1,211 @@
+"""GPU: the reference-facing Python surface (autograd operators, MaxK nonlinearity, DirectMaxKKernels)
+against the golden vectors produced by the reference's own code and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_close, graph_cuda, graph_np, make_problem
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ref_py():
+    return np.load(os.path.join(GOLD, "ref_py.npz"))
+
+
+@pytest.fixture(scope="module")
+def ref_cuda():
+    return np.load(os.path.join(GOLD, "ref_cuda.npz"))
+
+
+def _t(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+# ---------------------------------------------------------------- golden: reference python operator
+def test_v1_operator_matches_reference_forward(ref_py):
+    """maxk_spgemm(...) == the reference's MaxKSpGEMMFunction.forward on the same inputs (its CPU branch)."""
+    from maxk_spgemm_function import MaxKSpmmWrapper, maxk_spgemm
+    ip, ix, va = _t(ref_py["indptr"]), _t(ref_py["indices"]), _t(ref_py["values"])
+    x, deg, k = _t(ref_py["x"]), _t(ref_py["in_deg"]), int(ref_py["k"])
+    w = MaxKSpmmWrapper("golden")
+    w.build_metadata(ip)
+    out = w.spmm(ix, va, x, k, in_degrees=deg)                       # warp4-driven, fused /in_degrees
+    assert_close(out, ref_py["spgemm_fwd_norm"], "v1 forward / in_degrees")
+    raw = maxk_spgemm(ix, va, x, k, None, 0, ip)                     # indptr-driven, no normalisation
+    assert_close(raw, ref_py["spgemm_fwd_raw"], "v1 forward raw")
+    assert w.num_warps * 4 == ref_py["warp4_small"].size
+    assert np.array_equal(w.warp4_metadata.cpu().numpy(), ref_py["warp4_small"])   # == generate_meta.py output
+
+
+@pytest.mark.parametrize("k", [8, 32])
+def test_maxk_and_optmaxk_match_reference_classes(ref_py, k):
+    from maxk_models_integrated import MaxK, OPTMaxK
+    x = _t(ref_py["maxk_x"]).requires_grad_(True)
+    up = _t(ref_py["maxk_up"])
+    y = MaxK.apply(x, k)
+    (g,) = torch.autograd.grad(y, x, up)
+    assert np.array_equal(y.detach().cpu().numpy(), ref_py["maxk_fwd_k%d" % k])
+    assert np.array_equal(g.cpu().numpy(), ref_py["maxk_bwd_k%d" % k])
+
+    yo, tv, ti = OPTMaxK.apply(x, k)
+    assert ti.dtype == torch.int64 and not ti.requires_grad
+    assert np.array_equal(yo.detach().cpu().numpy(), ref_py["optmaxk_fwd_k%d" % k])
+    # same (value, index) pairs as torch.topk, row order is ours
+    order = np.argsort(-tv.detach().cpu().numpy(), axis=1, kind="stable")
+    assert np.array_equal(np.take_along_axis(tv.detach().cpu().numpy(), order, 1), ref_py["optmaxk_vals_k%d" % k])
+    assert np.array_equal(np.take_along_axis(ti.cpu().numpy(), order, 1), ref_py["optmaxk_idx_k%d" % k])
+    up_v_sorted = ref_py["optmaxk_upv_k%d" % k]
+    inv = np.argsort(order, axis=1)
+    up_v = _t(np.take_along_axis(up_v_sorted, inv, 1))                # same upstream grads, permuted to our row order
+    OPTMaxK.reference_compat = True
+    try:
+        (gc,) = torch.autograd.grad([yo, tv], x, [up, up_v], retain_graph=True)
+        assert np.array_equal(gc.cpu().numpy(), ref_py["optmaxk_bwd_k%d" % k])     # reference drops grad_topk_values
+    finally:
+        OPTMaxK.reference_compat = False
+    (gf,) = torch.autograd.grad([yo, tv], x, [up, up_v])
+    full = ref_py["optmaxk_bwd_k%d" % k] + oracle.scatter_dense(up_v_sorted, ref_py["optmaxk_idx_k%d" % k])
+    assert_close(gf, full, "OPTMaxK backward incl. grad_topk_values")
+
+
+# ------------------------------------------------------------------- golden: reference CUDA kernels
+@pytest.mark.parametrize("name", ["k32", "k64"])
+def test_entry_points_match_reference_cuda_kernels(ref_cuda, name):
+    import maxk_cuda_kernels as kern
+    g = {key[len(name) + 1:]: ref_cuda[key] for key in ref_cuda.files if key.startswith(name + "_")}
+    k = g["data"].shape[1]
+    w4 = _t(g["warp4"])
+    out = kern.spmm_maxk_forward(w4, _t(g["indices"]), _t(g["values"]), _t(g["data"]), _t(g["sel"]), w4.numel() // 4, k)
+    assert_close(out, g["fwd"], "spmm_maxk_forward vs reference kernel")
+    gs = kern.spmm_maxk_backward(w4, _t(g["indices"]), _t(g["values"]), _t(g["grad"]), _t(g["sel"]), w4.numel() // 4, k)
+    assert_close(gs, g["bwd"], "spmm_maxk_backward vs reference kernel", rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------ autograd end to end
+@pytest.mark.parametrize("k", [16, 32])
+def test_v1_autograd_forward_backward(k):
+    from maxk_spgemm_function import MaxKSpmmWrapper
+    p = make_problem(800, 30000, k, kind="powerlaw", seed=k, signed=True)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    deg = np.maximum(np.diff(ip), 1).astype(np.float32)
+    d = _t(deg)
+    x = p["x"].cuda().requires_grad_(True)
+    w = MaxKSpmmWrapper()
+    w.build_metadata(cip)
+    out = w.spmm(cix, cva, x, k, cip, d, d)
+    up = p["grad"].cuda()
+    out.backward(up)
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, p["cbsr_val"], p["cbsr_sel"], deg=deg), "v1 fwd")
+    gs = oracle.sspmm_bwd(ip, ix, va, p["grad"].numpy(), p["cbsr_sel"], deg=deg)
+    assert_close(x.grad, oracle.scatter_dense(gs, p["cbsr_col"]), "v1 grad wrt input_features")
+    assert x.grad.shape == (800, 256)
+
+
+def test_v1_k_not_smaller_than_dim_keeps_every_feature():
+    from maxk_spgemm_function import maxk_spgemm
+    p = make_problem(300, 4000, 8, seed=1)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    x = p["x"].cuda()
+    out = maxk_spgemm(cix, cva, x, 256, None, 0, cip)
+    ident = np.tile(np.arange(256, dtype=np.uint8), (300, 1))
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, p["x"].numpy(), ident), "k == D", rtol=2e-5)
+
+
+def test_v4_operator_with_precomputed_topk():
+    from maxk_models_integrated import OPTMaxK
+    from spgemmfunction_v4 import MaxKSpmmWrapper
+    k = 32
+    p = make_problem(600, 25000, k, kind="uniform", seed=4, signed=True)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    deg = np.maximum(np.diff(ip), 1).astype(np.float32)
+    x = p["x"].cuda().requires_grad_(True)
+    _, tv, ti = OPTMaxK.apply(x, k)
+    w = MaxKSpmmWrapper("g")
+    w.build_metadata(cip)
+    out = w.spmm(cix, cva, tv, ti, cip, _t(deg))
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, p["cbsr_val"], p["cbsr_sel"], deg=deg), "v4 fwd")
+    out.backward(p["grad"].cuda())
+    gs = oracle.sspmm_bwd(ip, ix, va, p["grad"].numpy(), p["cbsr_sel"], deg=deg)
+    assert_close(x.grad, oracle.scatter_dense(gs, p["cbsr_col"]), "v4 grad reaches x through OPTMaxK")
+    # torch.topk output (int64, value order) is accepted as well
+    tv2, ti2 = torch.topk(p["x"].cuda(), k, dim=1)
+    out2 = w.spmm(cix, cva, tv2, ti2, cip, _t(deg))
+    assert_close(out2, out.detach().cpu().numpy(), "v4 fwd with torch.topk inputs", rtol=2e-5)
+
+
+def test_gradcheck_like_adjoint_identity():
+    """<fwd(x_vals), g> == <x_vals, bwd(g)> on the GPU kernels themselves."""
+    import maxk_cuda_kernels as kern
+    p = make_problem(700, 40000, 32, kind="powerlaw", seed=8, signed=True)
+    cip, cix, cva = graph_cuda(p["graph"])
+    data, sel, g = _t(p["cbsr_val"]), _t(p["cbsr_sel"]), p["grad"].cuda()
+    out = kern.spgemm_forward_csr(cip[:-1], cip[1:], cix, cva, data, sel)
+    gs = kern.sspmm_backward_csr(cip[:-1], cip[1:], cix, cva, g, sel)
+    lhs, rhs = float((out.double() * g.double()).sum()), float((data.double() * gs.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+
+
+# ------------------------------------------------------------------------------ DirectMaxKKernels
+def test_direct_kernel_interface(tmp_path, monkeypatch):
+    from direct_kernel_interface import DirectMaxKKernels
+    from graph_loader import GraphDataLoader, save_warp4, warp4_path
+    p = make_problem(500, 20000, 32, seed=6)
+    monkeypatch.chdir(tmp_path)
+    loader = GraphDataLoader("kernels/graphs/")
+    loader.save_graph("toy", p["graph"]["indptr"], p["graph"]["indices"])
+    gd = loader.to_cuda_tensors(loader.load_graph("toy"))
+    dk = DirectMaxKKernels("toy")
+    assert dk.load_warp4_metadata() is False                          # no file yet, like the reference
+    with pytest.raises(RuntimeError):
+        dk.run_forward_kernel(gd, p["x"].cuda(), 32, timing=False)
+    quads, _ = oracle.warp4(p["graph"]["indptr"].numpy(), 64)
+    save_warp4(warp4_path("toy"), quads)
+    assert dk.load_warp4_metadata() is True and dk.num_warps == quads.size // 4
+    x = p["x"].cuda()
+    for cuda_topk in (True, False):
+        assert dk.validate_against_cusparse(gd, x, 32, use_cuda_topk=cuda_topk)
+        assert dk.last_validation["max_error"] < 1e-4
+    out, ms = dk.run_forward_kernel(gd, x, 32, timing=True)
+    vals, cols = oracle.topk(p["x"].numpy(), 32, 0)
+    assert_close(out, oracle.spgemm_fwd(gd["indptr"].cpu().numpy(), gd["indices"].cpu().numpy(), gd["values"].cpu().numpy(),
+                                        vals, cols.astype(np.uint8)), "DirectMaxKKernels forward")
+    assert ms > 0
+    gi, ms_b = dk.run_backward_kernel(gd, p["grad"].cuda(), 32, timing=True)
+    assert gi.shape == (500, 32) and ms_b > 0
+    res = dk.benchmark_all_k_values(gd, k_values=[16, 32, 64, 96], verbose=False)
+    assert sorted(res) == [16, 32, 64] and all(v["forward_time"] > 0 for v in res.values())
+    dk2 = DirectMaxKKernels("toy")
+    dk2.build_warp4_metadata(gd)
+    assert torch.equal(dk2.warp4_metadata, dk.warp4_metadata)
+
+
+def test_reference_smoke_shape_and_bug_repro_ks():
+    """V=1000, E=5000 random graph (maxk_spgemm_function.py:279-286) and the k values of test_bug.py:16-20:
+    the reference's uint8 top-k faults for k in {8,16,18}; ours is exact for every k."""
+    import maxk_cuda_kernels as kern
+    torch.manual_seed(42)
+    x = torch.rand(3349, 256, device="cuda")
+    for k in (8, 16, 18, 19, 20, 32):
+        v, i = kern.cuda_topk_maxk_float(x, k)
+        tv, ti = torch.topk(x, k, dim=1)
+        assert torch.equal(v, tv) and torch.equal(x.gather(1, i.long()), v)
+        tie_free = (tv[:, 1:] != tv[:, :-1]).all(dim=1)       # torch.rand has 2^-24 granularity: a few rows tie
+        assert tie_free.float().mean() > 0.9 and torch.equal(i.long()[tie_free], ti[tie_free])
+    xu = (x * 255).round().to(torch.uint8)
+    v8, i8 = kern.cuda_topk_maxk(xu, 32)
+    ev, ec = oracle.topk(xu.float().cpu().numpy(), 32, 0)
+    assert v8.dtype == torch.uint8 and np.array_equal(v8.cpu().numpy(), ev.astype(np.uint8))
+    assert np.array_equal(i8.cpu().numpy(), ec.astype(np.uint8))
+    sel = kern.generate_sparse_selector(100, 256, 32)
+    assert sel.shape == (100, 32) and sel.dtype == torch.uint8
+    assert all(len(set(r.tolist())) == 32 for r in sel.cpu())

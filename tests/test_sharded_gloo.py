@@ -1,0 +1,109 @@
+"""CPU, world_size 2 on gloo: the row-sharded layer (partition + collectives) against the single-process oracle.
+
+The compute backend injected here is the oracle (tests may do that); the product default is the CUDA
+backend, covered by tests/test_gpu_sharded.py on real GPUs.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from helpers import assert_close
+from sharded import ShardedMaxKAggregation, shard_columns, shard_rows, sharded_maxk_spgemm, slab_rows
+from synth_graphs import synth_graph
+
+
+class OracleCompute:
+    def topk(self, x, k):
+        v, c = oracle.topk(x.numpy(), k, 2)
+        return torch.from_numpy(v), torch.from_numpy(c.astype(np.uint8))
+
+    def spgemm(self, g, vals, sel, row_div=None):
+        out = oracle.spgemm_fwd(g["indptr"].numpy(), g["indices"].numpy(), g["values"].numpy(), vals.numpy(), sel.numpy(),
+                                deg=None if row_div is None else row_div.numpy())
+        return torch.from_numpy(out)
+
+    def sspmm(self, g, grad, sel, row_div=None):
+        gs = oracle.sspmm_bwd(g["indptr"].numpy(), g["indices"].numpy(), g["values"].numpy(), grad.numpy(), sel.numpy(),
+                              deg=None if row_div is None else row_div.numpy())
+        return torch.from_numpy(gs)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem(n=203, e=4000, k=16):
+    g = synth_graph(n, e, seed=11, kind="powerlaw")
+    gen = torch.Generator().manual_seed(3)
+    x, grad = torch.randn(n, 256, generator=gen), torch.rand(n, 256, generator=gen)
+    deg = torch.clamp((g["indptr"][1:] - g["indptr"][:-1]).float(), min=1)
+    return g, x, grad, deg, k
+
+
+def _worker(rank, world, port, mode, use_div, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, x, grad, deg, k = _problem()
+        n, m = g["v_num"], slab_rows(g["v_num"], world)
+        layer = ShardedMaxKAggregation(g, k, backward_mode=mode, compute=OracleCompute(), row_div=deg if use_div else None)
+        lo = rank * m
+        x_local, g_local = torch.zeros(m, 256), torch.zeros(m, 256)
+        rows = max(0, min(n, lo + m) - lo)
+        x_local[:rows], g_local[:rows] = x[lo:lo + rows], grad[lo:lo + rows]
+        xl = x_local.clone().requires_grad_(True)
+        out = sharded_maxk_spgemm(xl, layer)
+        out.backward(g_local)
+        gs = layer.backward(g_local)
+        np.savez(os.path.join(result_dir, "rank%d.npz" % rank), out=out.detach().numpy(), gs=gs.numpy(),
+                 xgrad=xl.grad.numpy(), wire_fwd=layer.wire_bytes()["forward"], wire_bwd=layer.wire_bytes()["backward"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,use_div", [("reduce_scatter", False), ("reduce_scatter", True), ("allgather", True)])
+def test_sharded_layer_matches_single_process_oracle(tmp_path, mode, use_div):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), mode, use_div, str(tmp_path)), nprocs=world, join=True)
+    g, x, grad, deg, k = _problem()
+    n, m = g["v_num"], slab_rows(g["v_num"], world)
+    ip, ix, va = (g[t].numpy() for t in ("indptr", "indices", "values"))
+    vals, cols = oracle.topk(x.numpy(), k, 2)
+    sel = cols.astype(np.uint8)
+    d = deg.numpy() if use_div else None
+    exp_out = oracle.spgemm_fwd(ip, ix, va, vals, sel, deg=d)
+    exp_gs = oracle.sspmm_bwd(ip, ix, va, grad.numpy(), sel, deg=d)
+    exp_xgrad = oracle.scatter_dense(exp_gs, cols)
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        lo, hi = rank * m, min(n, rank * m + m)
+        assert_close(r["out"][: hi - lo], exp_out[lo:hi], "rank %d forward" % rank)
+        assert_close(r["gs"][: hi - lo], exp_gs[lo:hi], "rank %d backward" % rank)
+        assert_close(r["xgrad"][: hi - lo], exp_xgrad[lo:hi], "rank %d autograd" % rank)
+        assert int(r["wire_fwd"]) == m * k * 5
+        assert int(r["wire_bwd"]) == (m * k * 4 if mode == "reduce_scatter" else m * 256 * 4)
+
+
+def test_partition_helpers_cover_the_graph_exactly():
+    g = synth_graph(101, 1500, seed=2)
+    for world in (1, 2, 4, 8):
+        m = slab_rows(101, world)
+        edges = 0
+        for rank in range(world):
+            r = shard_rows(g, world, rank)
+            assert r["indptr"].numel() == m + 1 and int(r["indptr"][-1]) == r["e_num"] == r["indices"].numel()
+            edges += r["e_num"]
+            c = shard_columns(g, world, rank)
+            assert c["indptr"].numel() == world * m + 1
+            if c["e_num"]:
+                assert int(c["indices"].min()) >= 0 and int(c["indices"].max()) < m
+        assert edges == 1500
+        assert sum(shard_columns(g, world, r)["e_num"] for r in range(world)) == 1500
