@@ -54,10 +54,11 @@ template <> struct EntryLoad<2> {
 // Edge accumulation for one row segment [b, e), visiting 32-edge batches
 // batch0, batch0+stride, ...   Fast path: k in {8, 16, 32, 64}.
 // ---------------------------------------------------------------------------------
-template <int K, int UNROLL>
+template <int K, int UNROLL, bool PREFETCHED>
 __device__ __forceinline__ void accumulate_fast(const int *__restrict__ idx, const float *__restrict__ val,
                                                 const float *__restrict__ cval, const uint8_t *__restrict__ csel,
-                                                float *acc, int b, int e, int batch0, int stride)
+                                                float *acc, int b, int e, int batch0, int stride, int first_c,
+                                                float first_w)
 {
     using LY = Lay<K>;
     constexpr int EPL = LY::EPL, L = LY::L, EPI = LY::EPI;
@@ -66,11 +67,15 @@ __device__ __forceinline__ void accumulate_fast(const int *__restrict__ idx, con
     float *acc_q = acc + q * L;
 
     int base = b + batch0 * 32;
-    int nxt_c = 0;
-    float nxt_w = 0.f;
-    if (base + lane < e) {
-        nxt_c = ld_stream_i32(idx + base + lane);
-        nxt_w = ld_stream_f32(val + base + lane);
+    int nxt_c = first_c;       // PREFETCHED: the caller already loaded the first batch of this row
+    float nxt_w = first_w;
+    if (!PREFETCHED) {
+        nxt_c = 0;
+        nxt_w = 0.f;
+        if (base + lane < e) {
+            nxt_c = ld_stream_i32(idx + base + lane);
+            nxt_w = ld_stream_f32(val + base + lane);
+        }
     }
     for (; base < e; base += stride * 32) {
         const int n = min(32, e - base);
@@ -144,12 +149,13 @@ __device__ __forceinline__ void accumulate_any_k(const int *__restrict__ idx, co
     }
 }
 
-template <int K>
+template <int K, bool PREFETCHED>
 __device__ __forceinline__ void accumulate_row(const int *idx, const float *val, const float *cval,
                                                const uint8_t *csel, float *acc, int k, int b, int e, int batch0,
-                                               int stride)
+                                               int stride, int first_c, float first_w)
 {
-    if constexpr (Lay<K>::kFast) accumulate_fast<K, 4>(idx, val, cval, csel, acc, b, e, batch0, stride);
+    if constexpr (Lay<K>::kFast)
+        accumulate_fast<K, 4, PREFETCHED>(idx, val, cval, csel, acc, b, e, batch0, stride, first_c, first_w);
     else accumulate_any_k(idx, val, cval, csel, acc, k, b, e, batch0, stride);
 }
 
@@ -221,14 +227,35 @@ spgemm_fwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row
             rb = __ldg(row_begin + first + lane);
             re = __ldg(row_end + first + lane);
         }
+        // software pipeline over the rows of the grab: the first CSR batch of row i+1 is in flight
+        // while row i is reduced (low-degree graphs are otherwise one DRAM latency per row)
+        int nb = __shfl_sync(kFullMask, rb, 0), ne = __shfl_sync(kFullMask, re, 0);
+        int pc = 0;
+        float pw = 0.f;
+        if (Lay<K>::kFast && ne - nb <= kLongRow && nb + lane < ne) {
+            pc = ld_stream_i32(idx + nb + lane);
+            pw = ld_stream_f32(val + nb + lane);
+        }
         for (int i = 0; i < nr; ++i) {
             const int r = first + i;
-            const int b = __shfl_sync(kFullMask, rb, i), e = __shfl_sync(kFullMask, re, i);
+            const int b = nb, e = ne;
+            const int cur_c = pc;
+            const float cur_w = pw;
+            if (i + 1 < nr) {
+                nb = __shfl_sync(kFullMask, rb, i + 1);
+                ne = __shfl_sync(kFullMask, re, i + 1);
+                pc = 0;
+                pw = 0.f;
+                if (Lay<K>::kFast && ne - nb <= kLongRow && nb + lane < ne) {
+                    pc = ld_stream_i32(idx + nb + lane);
+                    pw = ld_stream_f32(val + nb + lane);
+                }
+            }
             if (e - b > kLongRow) {
                 if (lane == 0) long_rows[atomicAdd(&ws->long_count, 1)] = r;
                 continue;
             }
-            if (e > b) accumulate_row<K>(idx, val, cval, csel, acc, k, b, e, 0, 1);
+            if (e > b) accumulate_row<K, true>(idx, val, cval, csel, acc, k, b, e, 0, 1, cur_c, cur_w);
             const bool has_div = row_div != nullptr;
             write_row<K>(acc, out + (size_t)r * dim, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
         }
@@ -262,7 +289,7 @@ spgemm_fwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict_
         if (item >= n_long) break;
         const int r = long_rows[item];
         const int b = row_begin[r], e = row_end[r];
-        accumulate_row<K>(idx, val, cval, csel, acc, k, b, e, warp, kLongWarps);
+        accumulate_row<K, false>(idx, val, cval, csel, acc, k, b, e, warp, kLongWarps, 0, 0.f);
         __syncthreads();
         float o = 0.f;
         if (threadIdx.x < kAccDim) o = sum_copies<K>(smem, threadIdx.x, threadIdx.x & 31, kLongWarps);

@@ -28,17 +28,25 @@ constexpr unsigned kFullB = 0xffffffffu;
 // banked layout of Lay<K>: every edge slot q gets its own copy living in banks [q*L, q*L+L), so
 // lanes of different edge slots never collide when they look their columns up.  The copies are
 // written in a lane-skewed order (32 distinct banks per store instruction).
+__device__ __forceinline__ void load_g_row(const float *__restrict__ g_row, int dim, float (&gv)[kAccDim / 32])
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int n = 0; n < kAccDim / 32; ++n) {
+        const int col = lane + 32 * n;
+        gv[n] = col < dim ? ld_stream_f32(g_row + col) : 0.f;
+    }
+}
+
 template <int K>
-__device__ __forceinline__ void stage_row(const float *__restrict__ g_row, float *gsm, int dim, bool has_div, float div)
+__device__ __forceinline__ void stage_row(const float (&gv)[kAccDim / 32], float *gsm, bool has_div, float div)
 {
     using LY = Lay<K>;
     const int lane = lane_id();
 #pragma unroll
     for (int n = 0; n < kAccDim / 32; ++n) {
-        const int col = lane + 32 * n;
-        float a = col < dim ? ld_stream_f32(g_row + col) : 0.f;
-        if (has_div) a /= div;
-        const int w0 = LY::word(col);
+        const float a = has_div ? gv[n] / div : gv[n];
+        const int w0 = LY::word(lane + 32 * n);
 #pragma unroll
         for (int q = 0; q < LY::EPI; ++q) gsm[w0 + ((q + lane / LY::L) % LY::EPI) * LY::L] = a;
     }
@@ -58,10 +66,11 @@ template <> struct SelLoad<2> {
 // Fast path, k in {8, 16, 32, 64}: a lane owns EPL consecutive entries of one destination row,
 // L = k/EPL lanes cover an edge, EPI = 32/L edges per warp instruction; one vector reduction
 // (16 B, or 8 B for k = 8) per lane per edge.
-template <int K, int UNROLL>
+template <int K, int UNROLL, bool PREFETCHED>
 __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const float *__restrict__ val,
                                              const uint8_t *__restrict__ csel, float *__restrict__ gs,
-                                             const float *gsm, int b, int e, int batch0, int stride)
+                                             const float *gsm, int b, int e, int batch0, int stride, int first_c,
+                                             float first_w)
 {
     using LY = Lay<K>;
     constexpr int EPL = LY::EPL, L = LY::L, EPI = LY::EPI;
@@ -70,11 +79,15 @@ __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const 
     const float *gsm_q = gsm + q * L;
 
     int base = b + batch0 * 32;
-    int nxt_c = 0;
-    float nxt_w = 0.f;
-    if (base + lane < e) {
-        nxt_c = ld_stream_i32(idx + base + lane);
-        nxt_w = ld_stream_f32(val + base + lane);
+    int nxt_c = first_c;       // PREFETCHED: the caller already loaded the first batch of this row
+    float nxt_w = first_w;
+    if (!PREFETCHED) {
+        nxt_c = 0;
+        nxt_w = 0.f;
+        if (base + lane < e) {
+            nxt_c = ld_stream_i32(idx + base + lane);
+            nxt_w = ld_stream_f32(val + base + lane);
+        }
     }
     for (; base < e; base += stride * 32) {
         const int n = min(32, e - base);
@@ -140,11 +153,13 @@ __device__ __forceinline__ void scatter_any_k(const int *__restrict__ idx, const
     }
 }
 
-template <int K>
+template <int K, bool PREFETCHED>
 __device__ __forceinline__ void scatter_row(const int *idx, const float *val, const uint8_t *csel, float *gs,
-                                            const float *gsm, int k, int b, int e, int batch0, int stride)
+                                            const float *gsm, int k, int b, int e, int batch0, int stride,
+                                            int first_c, float first_w)
 {
-    if constexpr (Lay<K>::kFast) scatter_fast<K, 4>(idx, val, csel, gs, gsm, b, e, batch0, stride);
+    if constexpr (Lay<K>::kFast)
+        scatter_fast<K, 4, PREFETCHED>(idx, val, csel, gs, gsm, b, e, batch0, stride, first_c, first_w);
     else scatter_any_k(idx, val, csel, gs, gsm, k, b, e, batch0, stride);
 }
 
@@ -170,9 +185,40 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
             rb = __ldg(row_begin + first + lane);
             re = __ldg(row_end + first + lane);
         }
+        // software pipeline over the rows of the grab: the gradient row and the first CSR batch of
+        // row i+1 are in flight while row i is scattered
+        int nb = __shfl_sync(kFullB, rb, 0), ne = __shfl_sync(kFullB, re, 0);
+        int pc = 0;
+        float pw = 0.f;
+        float pg[kAccDim / 32];
+        if (ne > nb && ne - nb <= kLongRow) {
+            load_g_row(g + (size_t)first * dim, dim, pg);
+            if (Lay<K>::kFast && nb + lane < ne) {
+                pc = ld_stream_i32(idx + nb + lane);
+                pw = ld_stream_f32(val + nb + lane);
+            }
+        }
         for (int i = 0; i < nr; ++i) {
             const int r = first + i;
-            const int b = __shfl_sync(kFullB, rb, i), e = __shfl_sync(kFullB, re, i);
+            const int b = nb, e = ne;
+            const int cur_c = pc;
+            const float cur_w = pw;
+            float cg[kAccDim / 32];
+#pragma unroll
+            for (int n = 0; n < kAccDim / 32; ++n) cg[n] = pg[n];
+            if (i + 1 < nr) {
+                nb = __shfl_sync(kFullB, rb, i + 1);
+                ne = __shfl_sync(kFullB, re, i + 1);
+                pc = 0;
+                pw = 0.f;
+                if (ne > nb && ne - nb <= kLongRow) {
+                    load_g_row(g + (size_t)(r + 1) * dim, dim, pg);
+                    if (Lay<K>::kFast && nb + lane < ne) {
+                        pc = ld_stream_i32(idx + nb + lane);
+                        pw = ld_stream_f32(val + nb + lane);
+                    }
+                }
+            }
             if (e <= b) continue;
             if (e - b > kLongRow) {
                 if (lane == 0) long_rows[atomicAdd(&ws->long_count, 1)] = r;
@@ -180,8 +226,8 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
             }
             const bool has_div = row_div != nullptr;
             __syncwarp();
-            stage_row<K>(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
-            scatter_row<K>(idx, val, csel, gs, gsm, k, b, e, 0, 1);
+            stage_row<K>(cg, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
+            scatter_row<K, true>(idx, val, csel, gs, gsm, k, b, e, 0, 1, cur_c, cur_w);
         }
     }
 }
@@ -207,8 +253,10 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
         const int r = long_rows[item];
         const int b = row_begin[r], e = row_end[r];
         const bool has_div = row_div != nullptr;
-        stage_row<K>(g + (size_t)r * dim, gsm, dim, has_div, has_div ? __ldg(row_div + r) : 1.f);
-        scatter_row<K>(idx, val, csel, gs, gsm, k, b, e, warp, kBwdLongWarps);
+        float gv[kAccDim / 32];
+        load_g_row(g + (size_t)r * dim, dim, gv);
+        stage_row<K>(gv, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
+        scatter_row<K, false>(idx, val, csel, gs, gsm, k, b, e, warp, kBwdLongWarps, 0, 0.f);
     }
 }
 

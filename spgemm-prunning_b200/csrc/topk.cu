@@ -37,14 +37,16 @@ __device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
     return __reduce_add_sync(kFullT, c);
 }
 
+// DIM256: dim == 256 (two 16-byte loads per lane, no padding logic).  ORDER: MAXK_ORDER_*.
+template <bool DIM256, int ORDER>
 __global__ void __launch_bounds__(kTopkThreads)
-topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, int order, int bank_mod,
+topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, int bank_mod,
                  float *__restrict__ out_val, uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32,
                  int64_t *__restrict__ out_i64, float *__restrict__ masked)
 {
-    __shared__ uint32_t s_key[kTopkWarps][kAccDim];
     __shared__ float s_val[kTopkWarps][kAccDim];
     __shared__ uint8_t s_col[kTopkWarps][kAccDim];
+    __shared__ uint32_t s_key[ORDER == MAXK_ORDER_VALUE_DESC ? kTopkWarps : 1][kAccDim];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
@@ -57,7 +59,7 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
     for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
         const float *row = x + r * dim;
         float v[8];
-        if (dim == kAccDim) {
+        if (DIM256) {
             const float4 a = ld_stream_f32x4(row + 4 * lane);
             const float4 b = ld_stream_f32x4(row + 128 + 4 * lane);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -73,7 +75,7 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         uint32_t kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const bool real = dim == kAccDim || col_of(lane, s) < dim;
+            const bool real = DIM256 || col_of(lane, s) < dim;
             key[s] = real ? order_key(v[s]) : 0u;   // pad: below every real key (real keys are >= 0x007fffff)
             kmax = max(kmax, key[s]);
             if (real) kmin = min(kmin, key[s]);
@@ -81,41 +83,60 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         kmax = __reduce_max_sync(kFullT, kmax);
         kmin = __reduce_min_sync(kFullT, kmin);
 
-        // ---- threshold: lo has count(>= lo) >= k, hi (exclusive, 33 bits) has count(>= hi) < k ---
-        uint32_t T = kmin;
-        if (count_ge(key, kmax) >= k) {
-            T = kmax;                            // rank k lies inside the run of maximal keys
-        } else {
-            uint32_t lo = kmin, hi = kmax;       // count(>= kmax) < k here
-            while (hi - lo > 1u) {
-                const uint32_t mid = lo + ((hi - lo) >> 1);
-                const int c = count_ge(key, mid);
-                if (c >= k) lo = mid; else hi = mid;
-                if (c == k) break;               // exactly k keys at or above mid: no tie at the boundary
+        // ---- threshold T with count(key > T) <= k <= count(key >= T) -------------------------------
+        // Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots alternate between
+        // linear interpolation of the count (few steps on smooth data) and plain bisection
+        // (guaranteed progress on anything); stops early when exactly k keys are at or above it.
+        uint32_t T;
+        bool exact = false;                      // exactly k keys >= T: no tie handling needed
+        {
+            int c_hi = count_ge(key, kmax);
+            if (c_hi >= k) {
+                T = kmax;                        // rank k lies inside the run of maximal keys
+                exact = (c_hi == k);
+            } else {
+                uint32_t lo = kmin, hi = kmax;
+                int c_lo = DIM256 ? kAccDim : dim;
+                bool interp = true;
+                while (hi - lo > 1u) {
+                    const uint32_t span = hi - lo;
+                    uint32_t mid = lo + (span >> 1);
+                    if (interp) {
+                        const float f = ((float)(c_lo - k) + 0.5f) * __frcp_rn((float)(c_lo - c_hi));
+                        const uint32_t off = (uint32_t)(f * (float)span);
+                        mid = lo + min(max(off, 1u), span - 1u);
+                    }
+                    interp = !interp;
+                    const int c = count_ge(key, mid);
+                    if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
+                    if (c == k) { exact = true; break; }
+                }
+                T = lo;
             }
-            T = lo;
         }
 
-        // ---- selection: key > T, plus the lowest-column keys == T until k -----------------------
-        unsigned b_gt[8], b_eq[8];
-        int gt_total = 0;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            b_gt[s] = __ballot_sync(kFullT, key[s] > T);
-            b_eq[s] = __ballot_sync(kFullT, key[s] == T);
-            gt_total += __popc(b_gt[s]);
-        }
-        const int need_eq = k - gt_total;        // >= 0; 0 only when the bisection stopped between two keys
-        // rank of my equal keys in column order: (half, lane, slot&3)
-        int eq_lo_before = 0, eq_lo_total = 0, eq_hi_before = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            eq_lo_before += __popc(b_eq[u] & lt);
-            eq_lo_total += __popc(b_eq[u]);
-            eq_hi_before += __popc(b_eq[u + 4] & lt);
-        }
+        // ---- selection flags ---------------------------------------------------------------------
         bool selb[8];
-        {
+        if (exact) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) selb[s] = key[s] >= T;
+        } else {
+            // ties straddle rank k: key > T always, key == T lowest column first, (half, lane, slot&3)
+            unsigned b_eq[8];
+            int gt_total = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                gt_total += __popc(__ballot_sync(kFullT, key[s] > T));
+                b_eq[s] = __ballot_sync(kFullT, key[s] == T);
+            }
+            const int need_eq = k - gt_total;
+            int eq_lo_before = 0, eq_lo_total = 0, eq_hi_before = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                eq_lo_before += __popc(b_eq[u] & lt);
+                eq_lo_total += __popc(b_eq[u]);
+                eq_hi_before += __popc(b_eq[u + 4] & lt);
+            }
             int rk = eq_lo_before;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
@@ -134,7 +155,7 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
 
         if (masked != nullptr) {
             float *mrow = masked + r * dim;
-            if (dim == kAccDim) {
+            if (DIM256) {
                 st_stream_f32x4(mrow + 4 * lane, make_float4(selb[0] ? v[0] : 0.f, selb[1] ? v[1] : 0.f,
                                                             selb[2] ? v[2] : 0.f, selb[3] ? v[3] : 0.f));
                 st_stream_f32x4(mrow + 128 + 4 * lane, make_float4(selb[4] ? v[4] : 0.f, selb[5] ? v[5] : 0.f,
@@ -148,28 +169,30 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             }
         }
 
-        // ---- output positions from the selection ballots ---------------------------------------
+        // ---- output positions from the selection ballots (popcounts only) ---------------------------
         unsigned bs[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) bs[s] = __ballot_sync(kFullT, selb[s]);
         int pos[8];
-        if (order == MAXK_ORDER_BANKED && bank_mod >= 4) {
+        if (ORDER == MAXK_ORDER_BANKED && bank_mod >= 4) {
             // class of (lane, slot) = 4*grp + (slot&3); classes ascending, columns ascending inside
-            int my_cnt = 0;
+            int c_lo[4], c_hi[4], mine = 0;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) my_cnt += selb[s] ? 1 : 0;
-            const int grp_total = __reduce_add_sync(cm, my_cnt);     // selected entries of my lane group
+            for (int u = 0; u < 4; ++u) {
+                c_lo[u] = __popc(bs[u] & cm);
+                c_hi[u] = __popc(bs[u + 4] & cm);
+                mine += c_lo[u] + c_hi[u];            // selected entries of my lane group
+            }
             int base = 0;
             for (int g = 0; g < groups - 1; ++g) {
-                const int tg = __shfl_sync(kFullT, grp_total, g);    // lane g belongs to group g
+                const int tg = __shfl_sync(kFullT, mine, g);    // lane g belongs to group g
                 if (g < grp) base += tg;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int c_lo = __popc(bs[u] & cm), c_hi = __popc(bs[u + 4] & cm);
                 pos[u] = base + __popc(bs[u] & cm & lt);
-                pos[u + 4] = base + c_lo + __popc(bs[u + 4] & cm & lt);
-                base += c_lo + c_hi;
+                pos[u + 4] = base + c_lo[u] + __popc(bs[u + 4] & cm & lt);
+                base += c_lo[u] + c_hi[u];
             }
         } else {
             // column order: (half, lane, slot&3)
@@ -188,19 +211,19 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             for (int s = 4; s < 8; ++s) { pos[s] = p; p += selb[s] ? 1 : 0; }
         }
 
-        // ---- stage the k entries in shared memory, then coalesced stores -----------------------
+        // ---- stage the k entries in shared memory, then coalesced stores ------------------------------
 #pragma unroll
         for (int s = 0; s < 8; ++s)
             if (selb[s]) {
                 s_val[warp][pos[s]] = v[s];
-                s_key[warp][pos[s]] = key[s];
                 s_col[warp][pos[s]] = (uint8_t)col_of(lane, s);
+                if (ORDER == MAXK_ORDER_VALUE_DESC) s_key[warp][pos[s]] = key[s];
             }
         __syncwarp();
 
         for (int i = lane; i < k; i += 32) {
             int dst = i;
-            if (order == MAXK_ORDER_VALUE_DESC) {
+            if (ORDER == MAXK_ORDER_VALUE_DESC) {
                 // rank sort: entries are staged in column order, so "earlier index" == "lower column"
                 const uint32_t ki = s_key[warp][i];
                 int rank = 0;
@@ -338,8 +361,21 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     if (dim == kAccDim && (((uintptr_t)x | (uintptr_t)masked) & 15)) return MAXK_ERR_ALIGN;
     if (order != MAXK_ORDER_VALUE_DESC && order != MAXK_ORDER_COLUMN_ASC && order != MAXK_ORDER_BANKED)
         return MAXK_ERR_SIZE;
-    topk_cbsr_kernel<<<grid_for_rows(n_rows), kTopkThreads, 0, (cudaStream_t)stream>>>(
-        x, n_rows, dim, k, order, banked_modulus(k), cbsr_val, cbsr_sel, idx_i32, idx_i64, masked);
+    const int grid = grid_for_rows(n_rows);
+    const int bm = banked_modulus(k);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MAXK_TOPK_LAUNCH(D256, ORD) \
+    topk_cbsr_kernel<D256, ORD><<<grid, kTopkThreads, 0, st>>>(x, n_rows, dim, k, bm, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked)
+    if (dim == kAccDim) {
+        if (order == MAXK_ORDER_VALUE_DESC) MAXK_TOPK_LAUNCH(true, MAXK_ORDER_VALUE_DESC);
+        else if (order == MAXK_ORDER_COLUMN_ASC || bm < 4) MAXK_TOPK_LAUNCH(true, MAXK_ORDER_COLUMN_ASC);
+        else MAXK_TOPK_LAUNCH(true, MAXK_ORDER_BANKED);
+    } else {
+        if (order == MAXK_ORDER_VALUE_DESC) MAXK_TOPK_LAUNCH(false, MAXK_ORDER_VALUE_DESC);
+        else if (order == MAXK_ORDER_COLUMN_ASC || bm < 4) MAXK_TOPK_LAUNCH(false, MAXK_ORDER_COLUMN_ASC);
+        else MAXK_TOPK_LAUNCH(false, MAXK_ORDER_BANKED);
+    }
+#undef MAXK_TOPK_LAUNCH
     return status_from_cuda(cudaGetLastError());
 }
 
