@@ -84,9 +84,10 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         kmin = __reduce_min_sync(kFullT, kmin);
 
         // ---- threshold T with count(key > T) <= k <= count(key >= T) -------------------------------
-        // Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots alternate between
-        // linear interpolation of the count (few steps on smooth data) and plain bisection
-        // (guaranteed progress on anything); stops early when exactly k keys are at or above it.
+        // Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots come from linear
+        // interpolation of the count (few steps on smooth data) with a plain bisection step whenever
+        // the same end moved twice in a row (guaranteed progress on anything); stops early when
+        // exactly k keys are at or above the pivot.
         uint32_t T;
         bool exact = false;                      // exactly k keys >= T: no tie handling needed
         {
@@ -97,17 +98,21 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             } else {
                 uint32_t lo = kmin, hi = kmax;
                 int c_lo = DIM256 ? kAccDim : dim;
-                bool interp = true;
+                int side = 0, repeat = 0;        // which end moved last and how often in a row
                 while (hi - lo > 1u) {
                     const uint32_t span = hi - lo;
                     uint32_t mid = lo + (span >> 1);
-                    if (interp) {
+                    if (repeat < 2) {            // secant step; a bisection step whenever one end is stuck
                         const float f = ((float)(c_lo - k) + 0.5f) * __frcp_rn((float)(c_lo - c_hi));
                         const uint32_t off = (uint32_t)(f * (float)span);
                         mid = lo + min(max(off, 1u), span - 1u);
+                    } else {
+                        repeat = 0;
                     }
-                    interp = !interp;
                     const int c = count_ge(key, mid);
+                    const int moved = c >= k ? 1 : 2;
+                    repeat = moved == side ? repeat + 1 : 0;
+                    side = moved;
                     if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
                     if (c == k) { exact = true; break; }
                 }
