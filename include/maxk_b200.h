@@ -109,6 +109,18 @@ int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_end,
                         const float *row_div,
                         void *workspace, size_t workspace_bytes, maxk_stream_t stream);
 
+/*
+ * Same as maxk_sspmm_backward but gs is NOT zero-filled: gs += the contribution of these rows.
+ * Lets a caller feed the source rows in slabs (e.g. while later slabs of g are still in flight
+ * from the host) -- zero gs once, then one call per slab with offset row pointers.
+ */
+int maxk_sspmm_backward_accumulate(const int32_t *row_begin, const int32_t *row_end,
+                                   const int32_t *indices, const float *values,
+                                   const float *g, const uint8_t *cbsr_sel,
+                                   float *gs, int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
+                                   const float *row_div,
+                                   void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+
 /* Scratch needed by (2) and (3) for a CSR with n_rows rows. */
 size_t maxk_spgemm_workspace_bytes(int64_t n_rows);
 

@@ -266,7 +266,7 @@ template <int K>
 static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const int *idx, const float *val,
                               const float *g, const uint8_t *csel, float *gs, int64_t n_rows, int64_t n_dst,
                               int64_t n_edges, int dim, int k, const float *row_div, SchedWorkspace *ws,
-                              cudaStream_t stream)
+                              bool zero_fill, cudaStream_t stream)
 {
     const size_t smem_main = (size_t)kBwdWarps * Lay<K>::kWords * sizeof(float);
     const size_t smem_long = (size_t)kBwdLongWarps * Lay<K>::kWords * sizeof(float);
@@ -284,8 +284,10 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
     int *long_rows = reinterpret_cast<int *>(ws + 1);
     cudaError_t err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
     if (err != cudaSuccess) return err;
-    err = cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream);
-    if (err != cudaSuccess) return err;
+    if (zero_fill) {
+        err = cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream);
+        if (err != cudaSuccess) return err;
+    }
     const int grid = sms * blocks_per_sm;
     const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kBwdWarps);
     sspmm_bwd_kernel<K><<<grid, kBwdThreads, smem_main, stream>>>(row_begin, row_end, idx, val, g, csel, gs, (int)n_rows, dim,
@@ -301,7 +303,7 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
 
 using namespace maxk;
 
-extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_end, const int32_t *indices,
+static int sspmm_backward_impl(bool zero_fill, const int32_t *row_begin, const int32_t *row_end, const int32_t *indices,
                                    const float *values, const float *g, const uint8_t *cbsr_sel, float *gs,
                                    int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
                                    const float *row_div, void *workspace, size_t workspace_bytes,
@@ -314,7 +316,7 @@ extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_
     if (n_dst == 0) return MAXK_OK;
     if (!gs) return MAXK_ERR_NULL;
     if (n_rows == 0 || n_edges == 0)
-        return status_from_cuda(cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream));
+        return zero_fill ? status_from_cuda(cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream)) : MAXK_OK;
     if (!row_begin || !row_end || !indices || !values || !g || !cbsr_sel || !workspace) return MAXK_ERR_NULL;
     if (workspace_bytes < maxk_spgemm_workspace_bytes(n_rows)) return MAXK_ERR_WORKSPACE;
     if (((uintptr_t)gs | (uintptr_t)workspace) & 15) return MAXK_ERR_ALIGN;
@@ -323,11 +325,31 @@ extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_
     SchedWorkspace *ws = reinterpret_cast<SchedWorkspace *>(workspace);
     cudaError_t err;
     switch (k) {
-        case 8: err = launch_bwd<8>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
-        case 16: err = launch_bwd<16>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
-        case 32: err = launch_bwd<32>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
-        case 64: err = launch_bwd<64>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
-        default: err = launch_bwd<0>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, stream); break;
+        case 8: err = launch_bwd<8>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        case 16: err = launch_bwd<16>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        case 32: err = launch_bwd<32>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        case 64: err = launch_bwd<64>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        default: err = launch_bwd<0>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
     }
     return status_from_cuda(err);
+}
+
+extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_end, const int32_t *indices,
+                                   const float *values, const float *g, const uint8_t *cbsr_sel, float *gs,
+                                   int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
+                                   const float *row_div, void *workspace, size_t workspace_bytes,
+                                   maxk_stream_t stream)
+{
+    return sspmm_backward_impl(true, row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim,
+                               k, row_div, workspace, workspace_bytes, stream);
+}
+
+extern "C" int maxk_sspmm_backward_accumulate(const int32_t *row_begin, const int32_t *row_end,
+                                              const int32_t *indices, const float *values, const float *g,
+                                              const uint8_t *cbsr_sel, float *gs, int64_t n_rows, int64_t n_dst,
+                                              int64_t n_edges, int dim, int k, const float *row_div, void *workspace,
+                                              size_t workspace_bytes, maxk_stream_t stream)
+{
+    return sspmm_backward_impl(false, row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim,
+                               k, row_div, workspace, workspace_bytes, stream);
 }

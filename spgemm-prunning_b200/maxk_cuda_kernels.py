@@ -44,6 +44,8 @@ _SIGNATURES = {
                                      _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_sspmm_backward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64,
                                      _c_int, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
+    "maxk_sspmm_backward_accumulate": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
+                                                _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_spgemm_workspace_bytes": (_c_size, [_c_i64]),
     "maxk_warp4_workspace_bytes": (_c_size, [_c_i64]),
     "maxk_warp4_scan": (_c_int, [_c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
@@ -167,8 +169,9 @@ def spgemm_forward_csr(row_begin, row_end, indices, values, cbsr_val, cbsr_sel, 
     return out
 
 
-def sspmm_backward_csr(row_begin, row_end, indices, values, grad_output, cbsr_sel, row_div=None, out=None):
-    """gs[n_dst, k] = sample_sel(A_csr^T (grad_output / row_div))."""
+def sspmm_backward_csr(row_begin, row_end, indices, values, grad_output, cbsr_sel, row_div=None, out=None,
+                       accumulate=False):
+    """gs[n_dst, k] = sample_sel(A_csr^T (grad_output / row_div)); accumulate=True adds into `out` instead."""
     row_begin = _cuda(row_begin, "row_begin", torch.int32)
     row_end = _cuda(row_end, "row_end", torch.int32)
     indices = _cuda(indices, "indices", torch.int32)
@@ -182,27 +185,37 @@ def sspmm_backward_csr(row_begin, row_end, indices, values, grad_output, cbsr_se
     if row_div is not None:
         row_div = _cuda(row_div, "row_div", torch.float32)
         _check(row_div.numel() == n_rows, "row_div must have one entry per row")
+    _check(not (accumulate and out is None), "accumulate=True needs an `out` tensor to add into")
     if out is None:
         out = torch.empty((n_dst, k), dtype=torch.float32, device=grad_output.device)
+    else:
+        _check(out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (n_dst, k),
+               "out must be a contiguous fp32 CUDA [n_dst, k] tensor")
+    fn = _lib.maxk_sspmm_backward_accumulate if accumulate else _lib.maxk_sspmm_backward
     with torch.cuda.device(grad_output.device):
         ws, ws_bytes = _workspace(n_rows, grad_output.device)
-        _status(_lib.maxk_sspmm_backward(_ptr(row_begin), _ptr(row_end), _ptr(indices), _ptr(values),
+        _status(fn(_ptr(row_begin), _ptr(row_end), _ptr(indices), _ptr(values),
                                          _ptr(grad_output), _ptr(cbsr_sel), _ptr(out), n_rows, n_dst,
                                          indices.numel(), dim, k, _ptr(row_div), _ptr(ws), ws_bytes,
                                          _stream(grad_output)), "maxk_sspmm_backward")
     return out
 
 
-def topk_cbsr(x, k, order=ORDER_BANKED, want_sel=True, want_i32=False, want_i64=False, want_masked=False):
-    """Exact row-wise top-k of x[N, D<=256] -> dict(values, sel, i32, i64, masked)."""
+def topk_cbsr(x, k, order=ORDER_BANKED, want_sel=True, want_i32=False, want_i64=False, want_masked=False,
+              out_values=None, out_sel=None):
+    """Exact row-wise top-k of x[N, D<=256] -> dict(values, sel, i32, i64, masked).
+    out_values / out_sel: optional preallocated contiguous [N, k] destinations (e.g. row slabs of a larger CBSR)."""
     x = _cuda(x, "input", torch.float32)
     _check(x.dim() == 2, "Input must be 2D tensor")
     n, d = x.shape
     _check(0 < k <= d, "Invalid k value")
     _check(d <= FULL_DIM, "feature dim must be <= 256 (uint8 column selectors)")
     dev = x.device
-    vals = torch.empty((n, k), dtype=torch.float32, device=dev)
-    sel = torch.empty((n, k), dtype=torch.uint8, device=dev) if want_sel else None
+    vals = out_values if out_values is not None else torch.empty((n, k), dtype=torch.float32, device=dev)
+    sel = out_sel if out_sel is not None else (torch.empty((n, k), dtype=torch.uint8, device=dev) if want_sel else None)
+    for t, dt, nm in ((vals, torch.float32, "out_values"), (sel, torch.uint8, "out_sel")):
+        _check(t is None or (t.is_cuda and t.is_contiguous() and t.dtype == dt and tuple(t.shape) == (n, k)),
+               nm + " must be a contiguous CUDA [N, k] tensor of the right dtype")
     i32 = torch.empty((n, k), dtype=torch.int32, device=dev) if want_i32 else None
     i64 = torch.empty((n, k), dtype=torch.int64, device=dev) if want_i64 else None
     masked = torch.empty((n, d), dtype=torch.float32, device=dev) if want_masked else None
