@@ -78,6 +78,21 @@ def _all_gather(local, group):
     return out
 
 
+def _all_gather_pair(a, b, group):
+    """Two all_gathers issued as ONE NCCL group launch (values + selectors of the CBSR slab)."""
+    world = dist.get_world_size(group)
+    out_a = a.new_empty((world * a.size(0),) + tuple(a.shape[1:]))
+    out_b = b.new_empty((world * b.size(0),) + tuple(b.shape[1:]))
+    if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+        with dist._coalescing_manager(group=group, device=a.device, async_ops=False):
+            dist.all_gather_into_tensor(out_a, a.contiguous(), group=group)
+            dist.all_gather_into_tensor(out_b, b.contiguous(), group=group)
+    else:
+        dist.all_gather_into_tensor(out_a, a.contiguous(), group=group)
+        dist.all_gather_into_tensor(out_b, b.contiguous(), group=group)
+    return out_a, out_b
+
+
 def _reduce_scatter_sum(full, group):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     m = full.size(0) // world
@@ -139,8 +154,7 @@ class ShardedMaxKAggregation:
     # x_local: [m, 256] (rows past the end of the graph are padding and may hold anything finite)
     def forward(self, x_local):
         vals, sel = self.compute.topk(x_local, self.k)
-        vals_full = _all_gather(vals, self.group)
-        self.sel_full = _all_gather(sel, self.group)
+        vals_full, self.sel_full = _all_gather_pair(vals, sel, self.group)
         return self.compute.spgemm(self.rows, vals_full, self.sel_full, self.row_div)
 
     def backward(self, grad_local):
