@@ -29,6 +29,17 @@ constexpr unsigned kFullT = 0xffffffffu;
 // Column owned by (lane, slot): slots 0-3 -> 4*lane+slot, slots 4-7 -> 128+4*lane+(slot-4).
 __device__ __forceinline__ int col_of(int lane, int slot) { return (slot < 4 ? 0 : 128) + 4 * lane + (slot & 3); }
 
+// Order-preserving key via one FADD: v + 0.0f turns -0 into +0 and every NaN into the canonical
+// positive quiet NaN 0x7fffffff (largest key), so no compare/select is needed per element.
+__device__ __forceinline__ uint32_t fast_key(float v)
+{
+    const uint32_t b = __float_as_uint(__fadd_rn(v, 0.0f));
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+
+// c_recip31[d] = floor(2^31 / d), d in [1, 256] (filled once by the host, see ensure_recip_table)
+__constant__ uint32_t c_recip31[kAccDim + 1];
+
 __device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
 {
     int c = 0;
@@ -76,7 +87,7 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const bool real = DIM256 || col_of(lane, s) < dim;
-            key[s] = real ? order_key(v[s]) : 0u;   // pad: below every real key (real keys are >= 0x007fffff)
+            key[s] = real ? fast_key(v[s]) : 0u;    // pad: below every real key (real keys are >= 0x007fffff)
             kmax = max(kmax, key[s]);
             if (real) kmin = min(kmin, key[s]);
         }
@@ -103,8 +114,10 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
                     const uint32_t span = hi - lo;
                     uint32_t mid = lo + (span >> 1);
                     if (repeat < 2) {            // secant step; a bisection step whenever one end is stuck
-                        const float f = ((float)(c_lo - k) + 0.5f) * __frcp_rn((float)(c_lo - c_hi));
-                        const uint32_t off = (uint32_t)(f * (float)span);
+                        // off = span * (c_lo - k + 1/2) / (c_lo - c_hi) in integers: counts are <= 256
+                        // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32)
+                        const uint32_t num = (uint32_t)(2 * (c_lo - k) + 1);
+                        const uint32_t off = __umulhi(span, num * c_recip31[c_lo - c_hi]);
                         mid = lo + min(max(off, 1u), span - 1u);
                     } else {
                         repeat = 0;
@@ -216,7 +229,8 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             for (int s = 4; s < 8; ++s) { pos[s] = p; p += selb[s] ? 1 : 0; }
         }
 
-        // ---- stage the k entries in shared memory, then coalesced stores ------------------------------
+        // ---- stage the k entries in shared memory (scattered 4-byte global stores measured slower),
+        //      then coalesced stores; the value order rank-sorts the staged entries on the way out
 #pragma unroll
         for (int s = 0; s < 8; ++s)
             if (selb[s]) {
@@ -229,7 +243,7 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         for (int i = lane; i < k; i += 32) {
             int dst = i;
             if (ORDER == MAXK_ORDER_VALUE_DESC) {
-                // rank sort: entries are staged in column order, so "earlier index" == "lower column"
+                // entries are staged in column order, so "earlier index" == "lower column"
                 const uint32_t ki = s_key[warp][i];
                 int rank = 0;
                 for (int j = 0; j < k; ++j) {
@@ -338,6 +352,18 @@ dense_spmm_kernel(const int *__restrict__ indptr, const int *__restrict__ idx, c
     }
 }
 
+static cudaError_t ensure_recip_table()
+{
+    static bool done = false;
+    if (done) return cudaSuccess;
+    uint32_t h[kAccDim + 1];
+    h[0] = 0;
+    for (int d = 1; d <= kAccDim; ++d) h[d] = (uint32_t)((1ull << 31) / (uint64_t)d);
+    const cudaError_t e = cudaMemcpyToSymbol(c_recip31, h, sizeof(h));
+    done = (e == cudaSuccess);
+    return e;
+}
+
 static int grid_for_rows(int64_t n_rows)
 {
     int dev = 0, sms = kNumSMsB200;
@@ -366,6 +392,10 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     if (dim == kAccDim && (((uintptr_t)x | (uintptr_t)masked) & 15)) return MAXK_ERR_ALIGN;
     if (order != MAXK_ORDER_VALUE_DESC && order != MAXK_ORDER_COLUMN_ASC && order != MAXK_ORDER_BANKED)
         return MAXK_ERR_SIZE;
+    {
+        const cudaError_t e = ensure_recip_table();
+        if (e != cudaSuccess) return status_from_cuda(e);
+    }
     const int grid = grid_for_rows(n_rows);
     const int bm = banked_modulus(k);
     cudaStream_t st = (cudaStream_t)stream;
