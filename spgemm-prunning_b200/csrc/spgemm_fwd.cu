@@ -193,22 +193,45 @@ __device__ __forceinline__ float sum_copies(const float *acc, int col, int lane,
 }
 
 // Row epilogue of the warp-owned path: sum the copies, re-zero them, fused divisor, one write.
+// Lane l owns columns l + 32 n.  word(l + 32 n) = word(l) + n * (32 / L) * 32, so every address is
+// a per-lane base + a compile-time offset: the 8 * EPI loads need no address arithmetic.
 template <int K>
 __device__ __forceinline__ void write_row(float *acc, float *__restrict__ out_row, int dim, bool has_div, float div)
 {
     using LY = Lay<K>;
     const int lane = lane_id();
+    constexpr int kColStep = (32 / LY::L) * 32;      // words between column c and column c + 32
+    const float *base = acc + LY::word(lane);
     float o[kAccDim / 32];
 #pragma unroll
-    for (int n = 0; n < kAccDim / 32; ++n) o[n] = sum_copies<K>(acc, lane + 32 * n, lane, 1);
+    for (int n = 0; n < kAccDim / 32; ++n) o[n] = 0.f;
+#pragma unroll
+    for (int q = 0; q < LY::EPI; ++q) {
+        const float *bq = base + ((q + lane / LY::L) % LY::EPI) * LY::L;   // lane-skewed copy: 32 distinct banks
+#pragma unroll
+        for (int n = 0; n < kAccDim / 32; ++n) o[n] += bq[n * kColStep];
+    }
     __syncwarp();
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
 #pragma unroll
     for (int i = 0; i < LY::kWords / 128; ++i) acc4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_div) {                                    // warp-uniform
+        const float r = 1.0f / div;
+        if (r != 0.f && fabsf(r) <= 3.0e38f) {        // normal divisor (degrees are >= 1): reciprocal path
 #pragma unroll
-    for (int n = 0; n < kAccDim / 32; ++n) {
-        const int col = lane + 32 * n;
-        if (col < dim) st_stream_f32(out_row + col, has_div ? o[n] / div : o[n]);
+            for (int n = 0; n < kAccDim / 32; ++n) o[n] = div_by_recip(o[n], div, r);
+        } else {                                      // zero / infinite / NaN divisor: plain IEEE division
+#pragma unroll
+            for (int n = 0; n < kAccDim / 32; ++n) o[n] = o[n] / div;
+        }
+    }
+    if (dim == kAccDim) {
+#pragma unroll
+        for (int n = 0; n < kAccDim / 32; ++n) st_stream_f32(out_row + lane + 32 * n, o[n]);
+    } else {
+#pragma unroll
+        for (int n = 0; n < kAccDim / 32; ++n)
+            if (lane + 32 * n < dim) st_stream_f32(out_row + lane + 32 * n, o[n]);
     }
     __syncwarp();
 }
@@ -315,7 +338,10 @@ spgemm_fwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict_
         __syncthreads();
         for (int i = threadIdx.x; i < kLongWarps * LY::kWords; i += kLongThreads) smem[i] = 0.f;
         if (threadIdx.x < dim) {
-            if (row_div != nullptr) o /= row_div[r];
+            if (row_div != nullptr) {
+                const float d = row_div[r];
+                o = div_by_recip(o, d, 1.0f / d);
+            }
             out[(size_t)r * dim + threadIdx.x] = o;
         }
     }

@@ -43,12 +43,26 @@ __device__ __forceinline__ void stage_row(const float (&gv)[kAccDim / 32], float
 {
     using LY = Lay<K>;
     const int lane = lane_id();
+    constexpr int kColStep = (32 / LY::L) * 32;      // words between column c and column c + 32
+    float a[kAccDim / 32];
 #pragma unroll
-    for (int n = 0; n < kAccDim / 32; ++n) {
-        const float a = has_div ? gv[n] / div : gv[n];
-        const int w0 = LY::word(lane + 32 * n);
+    for (int n = 0; n < kAccDim / 32; ++n) a[n] = gv[n];
+    if (has_div) {                                    // warp-uniform; one reciprocal per row (maxk_common.cuh)
+        const float r = 1.0f / div;
+        if (r != 0.f && fabsf(r) <= 3.0e38f) {        // normal divisor (degrees are >= 1): reciprocal path
 #pragma unroll
-        for (int q = 0; q < LY::EPI; ++q) gsm[w0 + ((q + lane / LY::L) % LY::EPI) * LY::L] = a;
+            for (int n = 0; n < kAccDim / 32; ++n) a[n] = div_by_recip(a[n], div, r);
+        } else {                                      // zero / infinite / NaN divisor: plain IEEE division
+#pragma unroll
+            for (int n = 0; n < kAccDim / 32; ++n) a[n] = a[n] / div;
+        }
+    }
+    float *base = gsm + LY::word(lane);
+#pragma unroll
+    for (int q = 0; q < LY::EPI; ++q) {
+        float *bq = base + ((q + lane / LY::L) % LY::EPI) * LY::L;         // lane-skewed copy: 32 distinct banks
+#pragma unroll
+        for (int n = 0; n < kAccDim / 32; ++n) bq[n * kColStep] = a[n];
     }
     __syncwarp();
 }
