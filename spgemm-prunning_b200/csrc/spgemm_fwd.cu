@@ -32,21 +32,21 @@ template <int EPL> struct EntryLoad;
 template <> struct EntryLoad<4> {
     float v[4];
     uint32_t s;
-    __device__ __forceinline__ void load(const float *cval, const uint8_t *csel, size_t off)
+    __device__ __forceinline__ void load(const float *cval, const uint8_t *csel, size_t off, uint64_t keep)
     {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(cval + off));
+        const float4 t = ld_keep_f32x4(cval + off, keep);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        s = __ldg(reinterpret_cast<const uint32_t *>(csel + off));
+        s = ld_keep_u32(csel + off, keep);
     }
 };
 template <> struct EntryLoad<2> {
     float v[2];
     uint32_t s;
-    __device__ __forceinline__ void load(const float *cval, const uint8_t *csel, size_t off)
+    __device__ __forceinline__ void load(const float *cval, const uint8_t *csel, size_t off, uint64_t keep)
     {
-        const float2 t = __ldg(reinterpret_cast<const float2 *>(cval + off));
+        const float2 t = ld_keep_f32x2(cval + off, keep);
         v[0] = t.x; v[1] = t.y;
-        s = __ldg(reinterpret_cast<const unsigned short *>(csel + off));
+        s = ld_keep_u16(csel + off, keep);
     }
 };
 
@@ -65,6 +65,7 @@ __device__ __forceinline__ void accumulate_fast(const int *__restrict__ idx, con
     const int lane = lane_id();
     const int q = lane / L, t = lane % L;
     float *acc_q = acc + q * L;
+    const uint64_t keep = policy_evict_last();     // CBSR rows are re-used ~degree times: keep them in L2
 
     int base = b + batch0 * 32;
     int nxt_c = first_c;       // PREFETCHED: the caller already loaded the first batch of this row
@@ -113,7 +114,7 @@ __device__ __forceinline__ void accumulate_fast(const int *__restrict__ idx, con
                 }
                 w[u] = __int_as_float(cwj.y);
                 ok[u] = ej < n;
-                if (ok[u]) ent[u].load(cval, csel, (size_t)cwj.x * K + EPL * t);
+                if (ok[u]) ent[u].load(cval, csel, (size_t)cwj.x * K + EPL * t, keep);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {

@@ -69,12 +69,12 @@ __device__ __forceinline__ void stage_row(const float (&gv)[kAccDim / 32], float
 
 template <int EPL> struct SelLoad;
 template <> struct SelLoad<4> {
-    __device__ static __forceinline__ uint32_t load(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
-    __device__ static __forceinline__ void red(float *p, const float *x) { red_add_f32x4(p, x[0], x[1], x[2], x[3]); }
+    __device__ static __forceinline__ uint32_t load(const uint8_t *p, uint64_t keep) { return ld_keep_u32(p, keep); }
+    __device__ static __forceinline__ void red(float *p, const float *x, uint64_t keep) { red_add_f32x4(p, x[0], x[1], x[2], x[3], keep); }
 };
 template <> struct SelLoad<2> {
-    __device__ static __forceinline__ uint32_t load(const uint8_t *p) { return __ldg(reinterpret_cast<const unsigned short *>(p)); }
-    __device__ static __forceinline__ void red(float *p, const float *x) { red_add_f32x2(p, x[0], x[1]); }
+    __device__ static __forceinline__ uint32_t load(const uint8_t *p, uint64_t keep) { return ld_keep_u16(p, keep); }
+    __device__ static __forceinline__ void red(float *p, const float *x, uint64_t keep) { red_add_f32x2(p, x[0], x[1], keep); }
 };
 
 // Fast path, k in {8, 16, 32, 64}: a lane owns EPL consecutive entries of one destination row,
@@ -91,6 +91,7 @@ __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const 
     const int lane = lane_id();
     const int q = lane / L, t = lane % L;
     const float *gsm_q = gsm + q * L;
+    const uint64_t keep = policy_evict_last();     // selectors and the sampled gradient are re-used: keep them in L2
 
     int base = b + batch0 * 32;
     int nxt_c = first_c;       // PREFETCHED: the caller already loaded the first batch of this row
@@ -127,7 +128,7 @@ __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const 
                 ok[u] = ej < n;
                 off[u] = (size_t)c * K + EPL * t;
                 s[u] = 0;
-                if (ok[u]) s[u] = SelLoad<EPL>::load(csel + off[u]);
+                if (ok[u]) s[u] = SelLoad<EPL>::load(csel + off[u], keep);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -135,7 +136,7 @@ __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const 
                     float x[EPL];
 #pragma unroll
                     for (int i = 0; i < EPL; ++i) x[i] = w[u] * gsm_q[LY::word((s[u] >> (8 * i)) & 0xff)];
-                    SelLoad<EPL>::red(gs + off[u], x);
+                    SelLoad<EPL>::red(gs + off[u], x, keep);
                 }
             }
         }
