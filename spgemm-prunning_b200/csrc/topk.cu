@@ -88,11 +88,27 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         for (int s = 0; s < 8; ++s) {
             const bool real = DIM256 || col_of(lane, s) < dim;
             key[s] = real ? fast_key(v[s]) : 0u;    // pad: below every real key (real keys are >= 0x007fffff)
-            kmax = max(kmax, key[s]);
-            if (real) kmin = min(kmin, key[s]);
         }
-        kmax = __reduce_max_sync(kFullT, kmax);
-        kmin = __reduce_min_sync(kFullT, kmin);
+        // Lower end of the search bracket.  Every lane has >= j keys at or above its own j-th largest
+        // key, so lo = min over lanes of that key has count(>= lo) >= 32 j >= k for j = ceil(k / 32):
+        // a far tighter start than the row minimum (U[0,1): ~90 keys above it instead of 256, and in
+        // the same binade as the threshold, where keys are linear in the value) -- the secant search
+        // then needs ~3 steps instead of ~7.
+        uint32_t m1 = max(key[0], key[1]), m2 = min(key[0], key[1]);
+#pragma unroll
+        for (int s = 2; s < 8; ++s) {
+            m2 = max(m2, min(m1, key[s]));
+            m1 = max(m1, key[s]);
+        }
+        kmax = __reduce_max_sync(kFullT, m1);
+        if (DIM256 && k <= 32) kmin = __reduce_min_sync(kFullT, m1);
+        else if (DIM256 && k <= 64) kmin = __reduce_min_sync(kFullT, m2);
+        else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (DIM256 || col_of(lane, s) < dim) kmin = min(kmin, key[s]);
+            kmin = __reduce_min_sync(kFullT, kmin);
+        }
 
         // ---- threshold T with count(key > T) <= k <= count(key >= T) -------------------------------
         // Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots come from linear
@@ -101,36 +117,35 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         // exactly k keys are at or above the pivot.
         uint32_t T;
         bool exact = false;                      // exactly k keys >= T: no tie handling needed
-        {
-            int c_hi = count_ge(key, kmax);
-            if (c_hi >= k) {
-                T = kmax;                        // rank k lies inside the run of maximal keys
-                exact = (c_hi == k);
-            } else {
-                uint32_t lo = kmin, hi = kmax;
-                int c_lo = DIM256 ? kAccDim : dim;
-                int side = 0, repeat = 0;        // which end moved last and how often in a row
-                while (hi - lo > 1u) {
-                    const uint32_t span = hi - lo;
-                    uint32_t mid = lo + (span >> 1);
-                    if (repeat < 2) {            // secant step; a bisection step whenever one end is stuck
-                        // off = span * (c_lo - k + 1/2) / (c_lo - c_hi) in integers: counts are <= 256
-                        // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32)
-                        const uint32_t num = (uint32_t)(2 * (c_lo - k) + 1);
-                        const uint32_t off = __umulhi(span, num * c_recip31[c_lo - c_hi]);
-                        mid = lo + min(max(off, 1u), span - 1u);
-                    } else {
-                        repeat = 0;
-                    }
-                    const int c = count_ge(key, mid);
-                    const int moved = c >= k ? 1 : 2;
-                    repeat = moved == side ? repeat + 1 : 0;
-                    side = moved;
-                    if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
-                    if (c == k) { exact = true; break; }
+        if (kmax == 0xffffffffu && count_ge(key, kmax) >= k) {
+            T = kmax;                            // (NaN rows only) rank k lies inside the run of maximal keys
+        } else {
+            // hi is exclusive: nothing is >= kmax + 1 (kmax = 0xffffffff keeps hi = kmax, whose count is < k here)
+            uint32_t lo = kmin, hi = kmax == 0xffffffffu ? kmax : kmax + 1u;
+            int c_lo = count_ge(key, lo);
+            int c_hi = kmax == 0xffffffffu ? count_ge(key, kmax) : 0;
+            int side = 0, repeat = 0;            // which end moved last and how often in a row
+            exact = (c_lo == k);
+            while (!exact && hi - lo > 1u) {
+                const uint32_t span = hi - lo;
+                uint32_t mid = lo + (span >> 1);
+                if (repeat < 2) {                // secant step; a bisection step whenever one end is stuck
+                    // off = span * (c_lo - k + 1/2) / (c_lo - c_hi) in integers: counts are <= 256
+                    // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32)
+                    const uint32_t num = (uint32_t)(2 * (c_lo - k) + 1);
+                    const uint32_t off = __umulhi(span, num * c_recip31[c_lo - c_hi]);
+                    mid = lo + min(max(off, 1u), span - 1u);
+                } else {
+                    repeat = 0;
                 }
-                T = lo;
+                const int c = count_ge(key, mid);
+                const int moved = c >= k ? 1 : 2;
+                repeat = moved == side ? repeat + 1 : 0;
+                side = moved;
+                if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
+                if (c == k) exact = true;
             }
+            T = lo;
         }
 
         // ---- selection flags ---------------------------------------------------------------------
