@@ -37,8 +37,11 @@ __device__ __forceinline__ uint32_t fast_key(float v)
     return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 
-// c_recip31[d] = floor(2^31 / d), d in [1, 256] (filled once by the host, see ensure_recip_table)
-__constant__ uint32_t c_recip31[kAccDim + 1];
+// c_recip31[d] = floor(2^31 / d), d in [1, 256]; statically initialised so that no host-side copy is
+// needed (the first call may happen inside a CUDA-graph capture)
+__constant__ uint32_t c_recip31[kAccDim + 1] = {
+#include "recip31_table.inc"
+};
 
 __device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
 {
@@ -367,18 +370,6 @@ dense_spmm_kernel(const int *__restrict__ indptr, const int *__restrict__ idx, c
     }
 }
 
-static cudaError_t ensure_recip_table()
-{
-    static bool done = false;
-    if (done) return cudaSuccess;
-    uint32_t h[kAccDim + 1];
-    h[0] = 0;
-    for (int d = 1; d <= kAccDim; ++d) h[d] = (uint32_t)((1ull << 31) / (uint64_t)d);
-    const cudaError_t e = cudaMemcpyToSymbol(c_recip31, h, sizeof(h));
-    done = (e == cudaSuccess);
-    return e;
-}
-
 static int grid_for_rows(int64_t n_rows)
 {
     int dev = 0, sms = kNumSMsB200;
@@ -407,10 +398,6 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     if (dim == kAccDim && (((uintptr_t)x | (uintptr_t)masked) & 15)) return MAXK_ERR_ALIGN;
     if (order != MAXK_ORDER_VALUE_DESC && order != MAXK_ORDER_COLUMN_ASC && order != MAXK_ORDER_BANKED)
         return MAXK_ERR_SIZE;
-    {
-        const cudaError_t e = ensure_recip_table();
-        if (e != cudaSuccess) return status_from_cuda(e);
-    }
     const int grid = grid_for_rows(n_rows);
     const int bm = banked_modulus(k);
     cudaStream_t st = (cudaStream_t)stream;

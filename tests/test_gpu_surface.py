@@ -228,3 +228,35 @@ def test_host_staged_pipeline_matches_device_resident_path():
     assert_close(hgs, oracle.sspmm_bwd(ip, ix, va, p["grad"].numpy(), p["cbsr_sel"]), "staged backward", rtol=2e-5)
     ref = kern.spgemm_forward_csr(cip[:-1], cip[1:], cix, cva, _t(p["cbsr_val"]), _t(p["cbsr_sel"]))
     assert torch.equal(hout.cuda(), ref)                 # the forward is deterministic, slab by slab too
+
+
+def test_layer_is_cuda_graph_capturable():
+    """top-k + forward + backward captured once in a CUDA graph and replayed on new inputs (no syncs, no
+    host copies, no default-stream work inside the calls)."""
+    import maxk_cuda_kernels as kern
+    p = make_problem(2000, 60000, 32, kind="powerlaw", seed=14, signed=True)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    x, g = p["x"].cuda(), p["grad"].cuda()
+    out, gs = torch.empty(2000, 256, device="cuda"), torch.empty(2000, 32, device="cuda")
+    vals, sel = torch.empty(2000, 32, device="cuda"), torch.empty(2000, 32, device="cuda", dtype=torch.uint8)
+
+    def step():
+        kern.topk_cbsr(x, 32, out_values=vals, out_sel=sel)
+        kern.spgemm_forward_csr(cip[:-1], cip[1:], cix, cva, vals, sel, out=out)
+        kern.sspmm_backward_csr(cip[:-1], cip[1:], cix, cva, g, sel, out=gs)
+
+    step()                                            # warm-up outside the capture (function attributes)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    x.copy_(torch.randn(2000, 256, generator=torch.Generator().manual_seed(99)))   # new inputs, same buffers
+    g.copy_(torch.rand(2000, 256, generator=torch.Generator().manual_seed(98)))
+    out.zero_(); gs.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    v2, c2 = oracle.topk(x.cpu().numpy(), 32, 2)
+    assert np.array_equal(sel.cpu().numpy(), c2.astype(np.uint8))
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, v2, c2.astype(np.uint8)), "graph replay forward")
+    assert_close(gs, oracle.sspmm_bwd(ip, ix, va, g.cpu().numpy(), c2.astype(np.uint8)), "graph replay backward", rtol=2e-5)
