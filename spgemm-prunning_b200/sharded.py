@@ -177,24 +177,91 @@ class ShardedMaxKAggregation:
 
 
 class _ShardedFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x_local, layer):
-        ctx.layer = layer
-        return layer.forward(x_local)
+    """x_local -> (x_local * topk_mask, A[rows_p, :] @ maxk(x)) with the selectors kept in ctx, so one
+    ShardedMaxKAggregation can serve every layer of a model."""
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def forward(ctx, x_local, layer):
+        vals, sel = layer.compute.topk(x_local, layer.k)
+        vals_full, sel_full = _all_gather_pair(vals, sel, layer.group)
+        out = layer.compute.spgemm(layer.rows, vals_full, sel_full, layer.row_div)
+        masked = torch.zeros_like(x_local).scatter_(1, sel.long(), vals)
+        ctx.layer = layer
+        ctx.save_for_backward(sel_full)
+        layer.sel_full = sel_full
+        return masked, out
+
+    @staticmethod
+    def backward(ctx, grad_masked, grad_out):
         layer = ctx.layer
-        gs = layer.backward(grad_out.contiguous())
+        (sel_full,) = ctx.saved_tensors
         lo = layer.rank * layer.m
-        sel_local = layer.sel_full[lo:lo + layer.m].contiguous()
-        if isinstance(layer.compute, CudaCompute):
-            dense = layer.compute.k.cbsr_scatter(gs, sel_local, dim=256)
-        else:
-            dense = torch.zeros(gs.size(0), 256, dtype=gs.dtype, device=gs.device).scatter_(1, sel_local.long(), gs)
-        return dense, None
+        sel_local = sel_full[lo:lo + layer.m].contiguous()
+        layer.sel_full = sel_full
+        gs = layer.backward(grad_out.contiguous())
+        dense = torch.zeros(gs.size(0), grad_masked.size(1), dtype=gs.dtype, device=gs.device)
+        dense.scatter_(1, sel_local.long(), gs)
+        mask = torch.zeros_like(grad_masked).scatter_(1, sel_local.long(), 1.0)
+        return grad_masked * mask + dense, None
+
+
+def sharded_maxk_act_spgemm(x_local, layer):
+    """Autograd entry point: (maxk(x_local), A[rows_p, :] @ maxk(x)) with gradients flowing to x_local."""
+    return _ShardedFn.apply(x_local, layer)
 
 
 def sharded_maxk_spgemm(x_local, layer):
-    """Autograd entry point: out_local = A[rows_p, :] @ maxk(x) with gradients flowing to x_local."""
-    return _ShardedFn.apply(x_local, layer)
+    """Aggregation only (the masked features are dropped)."""
+    return _ShardedFn.apply(x_local, layer)[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# Row-sharded GraphSAGE (BASELINE.json config 5: "GraphSAGE MaxK k=32 row-sharded at 2/4/8 B200 with
+# NCCL allgather of CBSR rows").  Same formulas as MaxKSAGE / MaxKSAGEConv (model_integrated_v3.py:62-192,
+# 522-591); every rank holds its row slab of the features and a full replica of the weights, whose
+# gradients are summed with one all_reduce per step (allreduce_gradients).
+# ------------------------------------------------------------------------------------------------
+class ShardedMaxKSAGE(torch.nn.Module):
+    def __init__(self, graph, in_size, hid_size, num_hid_layers, out_size, maxk=32, feat_drop=0.0, norm=False,
+                 group=None, compute=None, backward_mode="reduce_scatter"):
+        super().__init__()
+        nn = torch.nn
+        deg = torch.clamp((graph["indptr"][1:] - graph["indptr"][:-1]).to(torch.float32), min=1.0)
+        self.agg = ShardedMaxKAggregation(graph, maxk, group=group, backward_mode=backward_mode, compute=compute,
+                                          row_div=deg)
+        self.group = group
+        self.fc_self = nn.ModuleList(nn.Linear(hid_size, hid_size) for _ in range(num_hid_layers))
+        self.fc_neigh = nn.ModuleList(nn.Linear(hid_size, hid_size, bias=False) for _ in range(num_hid_layers))
+        self.norms = nn.ModuleList(nn.LayerNorm(hid_size) for _ in range(num_hid_layers if norm else 0))
+        self.drop = nn.Dropout(feat_drop)
+        self.lin_in = nn.Linear(in_size, hid_size)
+        self.lin_out = nn.Linear(hid_size, out_size)
+        gain = nn.init.calculate_gain("relu")
+        for a, b in zip(self.fc_self, self.fc_neigh):
+            nn.init.xavier_uniform_(a.weight, gain=gain)
+            nn.init.xavier_uniform_(b.weight, gain=gain)
+        nn.init.xavier_uniform_(self.lin_in.weight)
+        nn.init.xavier_uniform_(self.lin_out.weight)
+
+    def forward(self, x_local):
+        """x_local: this rank's row slab [m, in_size] (rows past the end of the graph are padding)."""
+        h = self.lin_in(x_local)
+        for i in range(len(self.fc_self)):
+            h_sparse, h_agg = sharded_maxk_act_spgemm(h, self.agg)
+            h = self.fc_self[i](self.drop(h_sparse)) + self.fc_neigh[i](h_agg)
+            if len(self.norms):
+                h = self.norms[i](h)
+        return self.lin_out(h)
+
+
+def allreduce_gradients(module, group=None):
+    """Sum the weight gradients over the ranks (each rank back-propagated the loss of its own rows)."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

@@ -14,7 +14,8 @@ import torch.multiprocessing as mp
 
 import oracle
 from helpers import assert_close
-from sharded import ShardedMaxKAggregation, shard_columns, shard_rows, sharded_maxk_spgemm, slab_rows
+from sharded import (ShardedMaxKAggregation, ShardedMaxKSAGE, allreduce_gradients, shard_columns, shard_rows,
+                     sharded_maxk_spgemm, slab_rows)
 from synth_graphs import synth_graph
 
 
@@ -107,3 +108,57 @@ def test_partition_helpers_cover_the_graph_exactly():
                 assert int(c["indices"].min()) >= 0 and int(c["indices"].max()) < m
         assert edges == 1500
         assert sum(shard_columns(g, world, r)["e_num"] for r in range(world)) == 1500
+
+
+# ------------------------------------------------------------------------------------ sharded GraphSAGE
+def _sage_reference(params, a, deg, x, k):
+    """Single-process restatement of ShardedMaxKSAGE.forward in plain torch (CPU)."""
+    h = x @ params["lin_in.weight"].t() + params["lin_in.bias"]
+    n_layers = sum(1 for key in params if key.startswith("fc_neigh."))
+    for i in range(n_layers):
+        v, c = oracle.topk(h.detach().numpy(), k, 2)
+        mask = torch.zeros_like(h).scatter_(1, torch.from_numpy(c.astype(np.int64)), 1.0)
+        hs = h * mask
+        agg = (a @ hs) / deg.unsqueeze(1)
+        h = hs @ params["fc_self.%d.weight" % i].t() + params["fc_self.%d.bias" % i] + agg @ params["fc_neigh.%d.weight" % i].t()
+    return h @ params["lin_out.weight"].t() + params["lin_out.bias"]
+
+
+def _sage_worker(rank, world, port, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, x, grad, deg, k = _problem(n=150, e=2500, k=16)
+        n, m = g["v_num"], slab_rows(g["v_num"], world)
+        torch.manual_seed(7)                                   # identical weights on every rank
+        model = ShardedMaxKSAGE(g, 256, 256, 2, 5, maxk=k, compute=OracleCompute())
+        lo = rank * m
+        rows = max(0, min(n, lo + m) - lo)
+        x_local = torch.zeros(m, 256)
+        x_local[:rows] = x[lo:lo + rows]
+        out = model(x_local)
+        out[:rows].square().sum().backward()                   # loss over the real rows of this rank
+        allreduce_gradients(model)
+        np.savez(os.path.join(result_dir, "sage%d.npz" % rank), out=out.detach().numpy(),
+                 **{"g_" + name: p.grad.numpy() for name, p in model.named_parameters()},
+                 **{"p_" + name: p.detach().numpy() for name, p in model.named_parameters()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sage_matches_single_process_model(tmp_path):
+    world = 2
+    mp.spawn(_sage_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g, x, grad, deg, k = _problem(n=150, e=2500, k=16)
+    n, m = g["v_num"], slab_rows(g["v_num"], world)
+    r0 = np.load(os.path.join(str(tmp_path), "sage0.npz"))
+    params = {key[2:]: torch.from_numpy(r0[key]).requires_grad_(True) for key in r0.files if key.startswith("p_")}
+    a = torch.sparse_csr_tensor(g["indptr"].long(), g["indices"].long(), g["values"], size=(n, n))
+    ref = _sage_reference(params, a, deg, x, k)
+    ref.square().sum().backward()
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "sage%d.npz" % rank))
+        lo, hi = rank * m, min(n, rank * m + m)
+        np.testing.assert_allclose(r["out"][: hi - lo], ref.detach().numpy()[lo:hi], rtol=2e-4, atol=2e-4)
+        for name, p in params.items():                      # summed over ranks == gradient of the full loss
+            np.testing.assert_allclose(r["g_" + name], p.grad.numpy(), rtol=2e-3, atol=2e-3, err_msg=name)
