@@ -208,3 +208,30 @@ def test_errors_are_loud(kern):
         kern.topk_cbsr(torch.rand(8, 300).cuda(), 32)   # uint8 selectors cannot address 300 columns
     with pytest.raises(RuntimeError):
         kern.load_warp4_metadata("no_such_graph")
+
+
+def test_c_abi_status_codes(kern):
+    """Argument errors come back as negative status codes from the C ABI itself (no launch)."""
+    import ctypes
+    lib = kern._lib
+    x = torch.rand(4, 256, device="cuda")
+    vals = torch.empty(4, 8, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    null = ctypes.c_void_p(0)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.maxk_topk_cbsr(P(x), 4, 256, 0, 2, P(vals), null, null, null, null, st) == -1      # MAXK_ERR_BAD_K
+    assert lib.maxk_topk_cbsr(P(x), 4, 300, 8, 2, P(vals), null, null, null, null, st) == -2      # MAXK_ERR_BAD_DIM
+    assert lib.maxk_topk_cbsr(null, 4, 256, 8, 2, P(vals), null, null, null, null, st) == -3      # MAXK_ERR_NULL
+    assert lib.maxk_topk_cbsr(P(x), 4, 256, 8, 7, P(vals), null, null, null, null, st) == -6      # bad order
+    assert lib.maxk_topk_cbsr(P(x), 0, 256, 8, 2, P(vals), null, null, null, null, st) == 0       # empty input is fine
+    ip = torch.zeros(5, dtype=torch.int32, device="cuda")
+    sel = torch.zeros(4, 8, dtype=torch.uint8, device="cuda")
+    out = torch.empty(4, 256, device="cuda")
+    ws = torch.empty(4096, dtype=torch.uint8, device="cuda")
+    args = (P(ip), ctypes.c_void_p(ip.data_ptr() + 4), null, null, P(vals), P(sel), P(out), 4, 0, 256, 8, null)
+    assert lib.maxk_spgemm_forward(*args, P(ws), 8, st) == -4                                      # workspace too small
+    assert lib.maxk_spgemm_forward(*args, ctypes.c_void_p(ws.data_ptr() + 4), 4000, st) == -5      # misaligned
+    assert lib.maxk_spgemm_forward(*args, P(ws), 4096, st) == 0
+    torch.cuda.synchronize()
+    assert float(out.abs().max()) == 0.0
+    assert "workspace" in lib.maxk_status_string(-4).decode()
