@@ -174,7 +174,7 @@ def workload_config(args, n, e):
                         "hidden %d, k=%d: top-k + fwd SpGEMM + bwd SSpMM" % (args.shape, n, e, DIM, args.k),
             "shape": args.shape, "nodes": n, "edges": e, "hidden": DIM, "k": args.k,
             "l2_note": "inputs per step (CSR 917 MB + features 239 MB + gradient 239 MB) exceed the 126 MB L2; no flush needed",
-            "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs, all_gather(CBSR) fwd, reduce_scatter bwd" % args.gpus}
+            "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs, all_gather(CBSR) fwd, %s bwd" % (args.gpus, args.bwd_mode)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -273,7 +273,7 @@ def run_ours(args, n, e):
         scaling = "strong"
     else:
         from sharded import ShardedMaxKAggregation, slab_rows
-        layer = ShardedMaxKAggregation(graph, k, backward_mode="reduce_scatter")
+        layer = ShardedMaxKAggregation(graph, k, backward_mode=args.bwd_mode)
         m = slab_rows(n, world)
         x = torch.rand(m, DIM, device=dev, generator=gen)
         grad = torch.rand(m, DIM, device=dev, generator=gen)
@@ -379,6 +379,8 @@ def main():
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--scale", type=float, default=1.0, help="developer knob: shrink the graph (not a contract bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bwd-mode", default="reduce_scatter", choices=["reduce_scatter", "allgather", "overlap"],
+                    help="multi-GPU backward exchange (sharded.py)")
     args = ap.parse_args()
     from synth_graphs import SHAPES
     n, e = SHAPES[args.shape]

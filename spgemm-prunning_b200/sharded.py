@@ -14,6 +14,11 @@ backward  : "reduce_scatter" (default): every rank scatters the outer products o
             "allgather" (the variant BASELINE.json names): all_gather the dense gradient rows
             [m, 256] -> [N, 256], then SSpMM over the rank's COLUMN slice A[:, rows_p]; no reduction,
             bit-reproducible, but 256/k times more bytes on the wire.
+            "overlap": same bytes as reduce_scatter, but the destinations are split into chunks of
+            consecutive owner ranks; the SSpMM of chunk c+1 runs while the partials of chunk c travel
+            (all_to_all on a second stream), and every owner sums the P blocks it received.  For
+            graphs whose partial gs is large (ogbn-products shape: 313 MB per rank) the collective
+            is as long as the kernel, so hiding it matters.
 
 The collectives and the partition logic are backend-agnostic (the CPU tests run them on gloo with
 world_size 2); the compute backend defaults to the CUDA kernels and there is no CPU fallback in the
@@ -93,6 +98,22 @@ def _all_gather_pair(a, b, group):
     return out_a, out_b
 
 
+def split_rows_by_destination(rows, boundaries):
+    """Per-row edge positions of the destination boundaries: pos[j][r] = first edge of row r whose
+    column is >= boundaries[j].  Needs columns sorted inside every row (returns None otherwise)."""
+    indptr, indices = rows["indptr"].long(), rows["indices"].long()
+    m = indptr.numel() - 1
+    if indices.numel() == 0:
+        return [indptr[:-1].to(torch.int32).clone() for _ in boundaries]
+    n_pad = int(max(int(indices.max()) + 1, max(boundaries))) + 1
+    row_of = torch.repeat_interleave(torch.arange(m, device=indices.device), indptr[1:] - indptr[:-1])
+    keys = row_of * n_pad + indices
+    if bool((keys[1:] < keys[:-1]).any()):
+        return None
+    base = torch.arange(m, device=indices.device) * n_pad
+    return [torch.searchsorted(keys, base + int(b)).to(torch.int32) for b in boundaries]
+
+
 def _reduce_scatter_sum(full, group):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     m = full.size(0) // world
@@ -127,13 +148,19 @@ class CudaCompute:
         ip = g["indptr"]
         return self.k.sspmm_backward_csr(ip[:-1], ip[1:], g["indices"], g["values"], grad, sel, row_div=row_div)
 
+    def sspmm_ranges(self, g, grad, sel, row_div, out):
+        """out += SSpMM over the per-row edge ranges [g['begin'], g['end'])."""
+        self.k.sspmm_backward_csr(g["begin"], g["end"], g["indices"], g["values"], grad, sel, row_div=row_div,
+                                  out=out, accumulate=True)
+
 
 class ShardedMaxKAggregation:
     """top-k -> all_gather(CBSR) -> SpGEMM, and its backward, for one rank's row slab."""
 
-    def __init__(self, graph, k, group=None, backward_mode="reduce_scatter", compute=None, row_div=None):
-        if backward_mode not in ("reduce_scatter", "allgather"):
-            raise ValueError("backward_mode must be 'reduce_scatter' or 'allgather'")
+    def __init__(self, graph, k, group=None, backward_mode="reduce_scatter", compute=None, row_div=None,
+                 overlap_chunks=4):
+        if backward_mode not in ("reduce_scatter", "allgather", "overlap"):
+            raise ValueError("backward_mode must be 'reduce_scatter', 'allgather' or 'overlap'")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -150,6 +177,17 @@ class ShardedMaxKAggregation:
             self.row_div = torch.ones(self.m, dtype=torch.float32, device=row_div.device)
             self.row_div[: hi - lo] = row_div[lo:hi]
         self.sel_full = None
+        self.chunks = None
+        if backward_mode == "overlap":
+            n_chunks = max(1, min(int(overlap_chunks), self.world))
+            owners = [list(range(c * self.world // n_chunks, (c + 1) * self.world // n_chunks)) for c in range(n_chunks)]
+            bounds = [o[0] * self.m for o in owners] + [self.world * self.m]
+            pos = split_rows_by_destination(self.rows, bounds)
+            if pos is None:                      # unsorted columns: the chunks are not contiguous edge ranges
+                self.backward_mode = "reduce_scatter"
+            else:
+                self.chunks = [{"owners": o, "begin": pos[c], "end": pos[c + 1]} for c, o in enumerate(owners)]
+                self.comm_stream = torch.cuda.Stream() if self.rows["indices"].is_cuda else None
 
     # x_local: [m, 256] (rows past the end of the graph are padding and may hold anything finite)
     def forward(self, x_local):
@@ -163,16 +201,49 @@ class ShardedMaxKAggregation:
         if self.backward_mode == "reduce_scatter":
             partial = self.compute.sspmm(self.rows, grad_local, self.sel_full, self.row_div)   # [P*m, k]
             return _reduce_scatter_sum(partial, self.group)
+        if self.backward_mode == "overlap":
+            return self._backward_overlap(grad_local)
         grad = grad_local if self.row_div is None else grad_local / self.row_div.unsqueeze(-1)
         grad_full = _all_gather(grad, self.group)                                             # [P*m, 256]
         lo = self.rank * self.m
         return self.compute.sspmm(self.cols, grad_full, self.sel_full[lo:lo + self.m].contiguous())
 
+    def _backward_overlap(self, grad_local):
+        """Chunked SSpMM + all_to_all: the partials of chunk c travel while chunk c+1 is computed."""
+        world, m, k = self.world, self.m, self.k
+        partial = torch.zeros(world * m, k, dtype=torch.float32, device=grad_local.device)
+        recv = torch.empty(world * m, k, dtype=torch.float32, device=grad_local.device)
+        cuda = grad_local.is_cuda
+        main = torch.cuda.current_stream() if cuda else None
+        if cuda:
+            self.comm_stream.wait_stream(main)
+        for ch in self.chunks:
+            sub = {"indptr": None, "begin": ch["begin"], "end": ch["end"], "indices": self.rows["indices"],
+                   "values": self.rows["values"]}
+            self.compute.sspmm_ranges(sub, grad_local, self.sel_full, self.row_div, partial)
+            lo, hi = ch["owners"][0] * m, (ch["owners"][-1] + 1) * m
+            in_split = [m if r in ch["owners"] else 0 for r in range(world)]
+            out_split = [m] * world if self.rank in ch["owners"] else [0] * world
+            out_buf = recv if self.rank in ch["owners"] else recv[:0]
+            if cuda:
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(done)
+                    dist.all_to_all_single(out_buf, partial[lo:hi], out_split, in_split, group=self.group)
+            else:
+                dist.all_to_all_single(out_buf, partial[lo:hi], out_split, in_split, group=self.group)
+        if cuda:
+            main.wait_stream(self.comm_stream)
+            partial.record_stream(self.comm_stream)
+            recv.record_stream(self.comm_stream)
+        return recv.view(world, m, k).sum(dim=0)
+
     def wire_bytes(self):
         """Bytes each rank RECEIVES per forward / backward (for the report)."""
         others = (self.world - 1) * self.m
         fwd = others * self.k * 5
-        bwd = others * self.k * 4 if self.backward_mode == "reduce_scatter" else others * 256 * 4
+        bwd = others * 256 * 4 if self.backward_mode == "allgather" else others * self.k * 4
         return {"forward": fwd, "backward": bwd}
 
 

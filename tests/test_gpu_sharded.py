@@ -75,13 +75,13 @@ def _check(tmp_path, world):
         assert_close(r["xgrad"][: hi - lo], exp_xgrad[lo:hi], "rank %d autograd" % rank, rtol=2e-5)
 
 
-@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather"])
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather", "overlap"])
 def test_world1_nccl(tmp_path, mode):
     mp.spawn(_run_rank, args=(1, _free_port(), mode, str(tmp_path)), nprocs=1, join=True)
     _check(tmp_path, 1)
 
 
-@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather"])
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather", "overlap"])
 def test_world2_nccl(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
