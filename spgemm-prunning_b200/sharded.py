@@ -24,8 +24,14 @@ The collectives and the partition logic are backend-agnostic (the CPU tests run 
 world_size 2); the compute backend defaults to the CUDA kernels and there is no CPU fallback in the
 product: `compute=` exists so that tests can inject the oracle.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# One NCCL group launch for the two all_gathers of a CBSR slab.  Measured on 8xB200: the coalesced
+# launch was SLOWER than two plain all_gathers (Reddit shape, P = 8: 1.60 vs 0.97 ms per step), so it is off.
+COALESCE_ALL_GATHER = os.environ.get("MAXK_COALESCE_ALL_GATHER", "0") == "1"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -88,7 +94,7 @@ def _all_gather_pair(a, b, group):
     world = dist.get_world_size(group)
     out_a = a.new_empty((world * a.size(0),) + tuple(a.shape[1:]))
     out_b = b.new_empty((world * b.size(0),) + tuple(b.shape[1:]))
-    if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+    if COALESCE_ALL_GATHER and dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
         with dist._coalescing_manager(group=group, device=a.device, async_ops=False):
             dist.all_gather_into_tensor(out_a, a.contiguous(), group=group)
             dist.all_gather_into_tensor(out_b, b.contiguous(), group=group)
