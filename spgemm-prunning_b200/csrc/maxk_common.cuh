@@ -139,15 +139,6 @@ __device__ __forceinline__ void red_add_f32x2(float *p, float a, float b, uint64
     asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(a), "f"(b), "l"(pol) : "memory");
 }
 
-// Order-preserving key: larger key <=> larger value; NaN largest; -0 == +0.
-__device__ __forceinline__ uint32_t order_key(float f)
-{
-    uint32_t b = __float_as_uint(f);
-    if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
-    if (b == 0x80000000u) b = 0u;
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-
 // x / d with one reciprocal per row instead of one IEEE division per element: q = x*r followed by one
 // residual correction (Markstein) is correctly rounded except in rare double-rounding cases (<= 1 ulp,
 // far inside the 1e-5 parity tolerance) and costs 3 FMA-pipe instructions instead of a ~30-instruction
