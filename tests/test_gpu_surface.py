@@ -260,3 +260,30 @@ def test_layer_is_cuda_graph_capturable():
     assert np.array_equal(sel.cpu().numpy(), c2.astype(np.uint8))
     assert_close(out, oracle.spgemm_fwd(ip, ix, va, v2, c2.astype(np.uint8)), "graph replay forward")
     assert_close(gs, oracle.sspmm_bwd(ip, ix, va, g.cpu().numpy(), c2.astype(np.uint8)), "graph replay backward", rtol=2e-5)
+
+
+def test_ops_run_on_the_current_stream_and_device():
+    """Launches go to torch's CURRENT stream (the reference uses the legacy default stream,
+    cuda_kernel_wrappers.cu:46) and to the tensors' device."""
+    import maxk_cuda_kernels as kern
+    p = make_problem(1500, 50000, 32, seed=21)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    side = torch.cuda.Stream()
+    x = p["x"].cuda()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        big = torch.empty(64 << 20, device="cuda").normal_()      # keeps `side` busy before our kernels
+        r = kern.topk_cbsr(x, 32)
+        out = kern.spgemm_forward_csr(cip[:-1], cip[1:], cix, cva, r["values"], r["sel"])
+        gs = kern.sspmm_backward_csr(cip[:-1], cip[1:], cix, cva, p["grad"].cuda(non_blocking=True), r["sel"])
+    side.synchronize()
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, p["cbsr_val"], p["cbsr_sel"]), "forward on a side stream")
+    assert_close(gs, oracle.sspmm_bwd(ip, ix, va, p["grad"].numpy(), p["cbsr_sel"]), "backward on a side stream")
+    del big
+    if torch.cuda.device_count() > 1:                              # tensors on cuda:1 while cuda:0 is current
+        d1 = torch.device("cuda", 1)
+        r1 = kern.topk_cbsr(x.to(d1), 32)
+        o1 = kern.spgemm_forward_csr(cip[:-1].to(d1), cip[1:].to(d1), cix.to(d1), cva.to(d1), r1["values"], r1["sel"])
+        torch.cuda.synchronize(d1)
+        assert o1.device == d1 and torch.equal(o1.cpu(), out.cpu())
