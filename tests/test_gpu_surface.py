@@ -189,6 +189,22 @@ def test_direct_kernel_interface(tmp_path, monkeypatch):
     assert torch.equal(dk2.warp4_metadata, dk.warp4_metadata)
 
 
+def test_generate_meta_writes_csr_and_csc_quads(tmp_path, monkeypatch):
+    """kernels/generate_meta.py + generate_meta_csc.py on the GPU: both files equal the oracle's quads."""
+    from graph_loader import GraphDataLoader, csr_to_csc, generate_meta
+    p = make_problem(700, 30000, 32, seed=8, kind="powerlaw")
+    monkeypatch.chdir(tmp_path)
+    GraphDataLoader("kernels/graphs/").save_graph("toy", p["graph"]["indptr"], p["graph"]["indices"])
+    p_csr, n_csr, p_csc, n_csc = generate_meta("toy")
+    ip = p["graph"]["indptr"].numpy()
+    want, w = oracle.warp4(ip, 64)
+    assert n_csr == w and np.array_equal(np.fromfile(p_csr, dtype=np.int32), want)
+    t_ptr, _ = csr_to_csc(p["graph"]["indptr"], p["graph"]["indices"])
+    want_t, w_t = oracle.warp4(t_ptr.numpy(), 64)
+    assert n_csc == w_t and np.array_equal(np.fromfile(p_csc, dtype=np.int32), want_t)
+    assert p_csc.endswith("w12_nz64_warp_4_csc/toy.warp4_csc")
+
+
 def test_reference_smoke_shape_and_bug_repro_ks():
     """V=1000, E=5000 random graph (maxk_spgemm_function.py:279-286) and the k values of test_bug.py:16-20:
     the reference's uint8 top-k faults for k in {8,16,18}; ours is exact for every k."""

@@ -76,3 +76,47 @@ def test_ops_refuse_cpu_tensors():
         maxk_spgemm(torch.zeros(1, dtype=torch.int32), torch.ones(1), x, 8, None, 0, torch.zeros(5, dtype=torch.int32))
     with pytest.raises(RuntimeError):
         k.load_warp4_metadata("definitely_missing_graph")
+
+
+def test_clean_edges_matches_dataset_gen_steps():
+    """dataset_gen.py:44-98: undirected -> self loops -> dedup, checked against a plain Python set."""
+    from graph_loader import clean_edges
+    rng = np.random.default_rng(5)
+    n = 300
+    src, dst = rng.integers(0, n, 4000), rng.integers(0, n, 4000)
+    src[:50], dst[:50] = src[50:100], dst[50:100]           # guaranteed multi-edges
+    indptr, indices = clean_edges(torch.from_numpy(src), torch.from_numpy(dst), n)
+    want = set(zip(src.tolist(), dst.tolist())) | set(zip(dst.tolist(), src.tolist())) | {(i, i) for i in range(n)}
+    rows = np.repeat(np.arange(n), np.diff(indptr.numpy()))
+    got = list(zip(rows.tolist(), indices.tolist()))
+    assert len(got) == len(set(got)) == len(want) and set(got) == want
+    assert indptr.dtype == torch.int32 and indices.dtype == torch.int32 and int(indptr[-1]) == len(want)
+    # directed, no loops: only dedup
+    ip2, ix2 = clean_edges(src, dst, n, undirected=False, self_loops=False)
+    assert int(ip2[-1]) == len(set(zip(src.tolist(), dst.tolist())))
+    e_ptr, e_idx = clean_edges([], [], 4)                      # empty edge list -> the identity pattern
+    assert e_ptr.tolist() == [0, 1, 2, 3, 4] and e_idx.tolist() == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        clean_edges([0, 5], [1, 1], 4)
+
+
+def test_csr_to_csc_matches_scipy():
+    from scipy.sparse import csr_matrix
+    from graph_loader import csr_to_csc
+    g = synth_graph(400, 9000, seed=3, kind="powerlaw")
+    ip, ix, va = g["indptr"].numpy(), g["indices"].numpy(), g["values"].numpy()
+    rows = np.repeat(np.arange(400), np.diff(ip))
+    t_ptr, t_idx, t_val = csr_to_csc(g["indptr"], g["indices"], g["values"])
+    dense = np.zeros((400, 400))
+    np.add.at(dense, (rows, ix), va.astype(np.float64))
+    t_rows = np.repeat(np.arange(400), np.diff(t_ptr.numpy()))
+    dense_t = np.zeros((400, 400))
+    np.add.at(dense_t, (t_rows, t_idx.numpy()), t_val.numpy().astype(np.float64))
+    assert np.array_equal(dense.T, dense_t)
+    ref = csr_matrix((np.ones(len(ix), np.float32), ix, ip), shape=(400, 400)).tocsc()   # generate_meta_csc.py:134-141
+    assert np.array_equal(t_ptr.numpy(), ref.indptr)
+    # a twice-transposed matrix is the original with sorted columns
+    b_ptr, b_idx = csr_to_csc(t_ptr, t_idx)
+    assert np.array_equal(b_ptr.numpy(), ip)
+    for r in (0, 7, 399):
+        assert np.array_equal(b_idx.numpy()[ip[r]:ip[r + 1]], np.sort(ix[ip[r]:ip[r + 1]]))
