@@ -143,6 +143,78 @@ def test_v4_operator_with_precomputed_topk():
     assert_close(out2, out.detach().cpu().numpy(), "v4 fwd with torch.topk inputs", rtol=2e-5)
 
 
+def test_v3_operator_csr_forward_csc_backward(tmp_path, monkeypatch):
+    """spgemmfunction_v3.py: CSR quads forward, CSC arrays + CSC quads backward, on a *directed* graph so that
+    a mix-up of the two sets of arrays cannot go unnoticed; metadata read from the files generate_meta writes."""
+    from graph_loader import GraphDataLoader, csr_to_csc, generate_meta
+    from spgemmfunction_v3 import MaxKSpGEMMFunction, MaxKSpmmWrapper
+    k = 16
+    p = make_problem(500, 20000, k, kind="powerlaw", seed=9, signed=True)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    t_ptr, t_idx, t_val = csr_to_csc(cip, cix, cva)
+    in_deg = np.maximum(np.diff(ip), 1).astype(np.float32)
+    out_deg = np.maximum(np.diff(t_ptr.cpu().numpy()), 1).astype(np.float32)
+    monkeypatch.chdir(tmp_path)
+    GraphDataLoader("kernels/graphs/").save_graph("toy", ip, ix)
+    generate_meta("toy")
+    w = MaxKSpmmWrapper("toy")
+    with pytest.raises(RuntimeError):
+        MaxKSpmmWrapper("absent").load_metadata()
+    assert w.load_metadata() and w.num_warps_csr > 0 and w.num_warps_csc > 0
+    x = p["x"].cuda().requires_grad_(True)
+    out = w.spmm(cix, cva, x, k, cip, _t(in_deg), _t(out_deg), t_idx, t_val)
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, p["cbsr_val"], p["cbsr_sel"], deg=in_deg), "v3 fwd")
+    out.backward(p["grad"].cuda())
+    # the kernel's formula on the CSC arrays (rows of A^T), gradient rows divided by out_degrees
+    tp, ti_, tv_ = t_ptr.cpu().numpy(), t_idx.cpu().numpy(), t_val.cpu().numpy()
+    gs = oracle.sspmm_bwd(tp, ti_, tv_, p["grad"].numpy(), p["cbsr_sel"], deg=out_deg)
+    assert_close(x.grad, oracle.scatter_dense(gs, p["cbsr_col"]), "v3 grad (CSC arrays + CSC quads)")
+    # reference_compat reproduces :118-119 (grad_output masked by the input's top-k pattern)
+    MaxKSpGEMMFunction.reference_compat = True
+    try:
+        x2 = p["x"].cuda().requires_grad_(True)
+        w.spmm(cix, cva, x2, k, cip, _t(in_deg), _t(out_deg), t_idx, t_val).backward(p["grad"].cuda())
+    finally:
+        MaxKSpGEMMFunction.reference_compat = False
+    mask = np.zeros((500, 256), np.float32)
+    np.put_along_axis(mask, p["cbsr_col"].astype(np.int64), 1.0, axis=1)
+    gs2 = oracle.sspmm_bwd(tp, ti_, tv_, p["grad"].numpy() * mask, p["cbsr_sel"], deg=out_deg)
+    assert_close(x2.grad, oracle.scatter_dense(gs2, p["cbsr_col"]), "v3 grad, reference_compat")
+
+
+def test_optimized_operator_matches_v4_on_an_undirected_graph():
+    """spgemmfunction.py: pre-computed top-k, CSC arrays with the CSR quads; on a symmetric graph (same row
+    order either way) it is the v4 result."""
+    from graph_loader import csr_to_csc
+    from maxk_models_integrated import OPTMaxK
+    from spgemmfunction import OptimizedMaxKSpmmWrapper
+    from spgemmfunction_v4 import MaxKSpmmWrapper as V4
+    from synth_graphs import symmetrize, synth_graph
+    k = 32
+    g = symmetrize(synth_graph(400, 6000, seed=11))
+    cip, cix, cva = g["indptr"].cuda(), g["indices"].cuda(), g["values"].cuda()
+    t_ptr, t_idx, t_val = csr_to_csc(cip, cix, cva)
+    assert torch.equal(t_ptr, cip) and torch.equal(t_idx, cix)
+    deg = (cip[1:] - cip[:-1]).clamp(min=1).float()
+    x = torch.randn(400, 256, generator=torch.Generator().manual_seed(2)).cuda()
+    up = torch.rand(400, 256, generator=torch.Generator().manual_seed(3)).cuda()
+    res = []
+    for make in (lambda: OptimizedMaxKSpmmWrapper("g"), lambda: V4("g")):
+        xi = x.clone().requires_grad_(True)
+        _, tv, ti = OPTMaxK.apply(xi, k)
+        w = make()
+        w.build_metadata(cip)
+        out = (w.spmm(cix, cva, tv, ti, cip, deg, deg, t_idx, t_val) if isinstance(w, OptimizedMaxKSpmmWrapper)
+               else w.spmm(cix, cva, tv, ti, cip, deg))
+        out.backward(up)
+        res.append((out.detach(), xi.grad))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        OptimizedMaxKSpmmWrapper("g").spmm(cix, cva, x[:, :k], None, cip, deg, deg, t_idx, t_val)
+
+
 def test_gradcheck_like_adjoint_identity():
     """<fwd(x_vals), g> == <x_vals, bwd(g)> on the GPU kernels themselves."""
     import maxk_cuda_kernels as kern
