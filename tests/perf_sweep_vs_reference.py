@@ -1,4 +1,5 @@
-"""Developer timing sweep (not the contract bench): ours vs the reference kernels recompiled for sm_100a."""
+"""Developer timing sweep (not the contract bench, not collected by pytest): ours vs the reference kernels
+recompiled for sm_100a (oracle/_ref).  Lives under tests/ because only test code may execute oracle/."""
 import argparse
 import os
 import sys
