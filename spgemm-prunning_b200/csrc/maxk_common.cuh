@@ -149,6 +149,15 @@ __device__ __forceinline__ float div_by_recip(float x, float d, float r)
     return fmaf(fmaf(-q, d, x), r, q);
 }
 
+// True when 1/d is a normal number, i.e. div_by_recip is usable; zero / infinite / NaN divisors (and
+// divisors so large that the reciprocal is denormal-flushed) take the plain IEEE division instead.
+__device__ __forceinline__ bool recip_usable(float r) { return r != 0.f && fabsf(r) <= 3.0e38f; }
+__device__ __forceinline__ float div_guarded(float x, float d)
+{
+    const float r = 1.0f / d;
+    return recip_usable(r) ? div_by_recip(x, d, r) : x / d;
+}
+
 inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? MAXK_OK : (int)e; }
 
 inline int device_sm_count()
@@ -157,6 +166,32 @@ inline int device_sm_count()
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return sms > 0 ? sms : kNumSMsB200;
+}
+
+// Launch configuration of a (main, long-row) kernel pair, cached per device: the opt-in dynamic shared
+// memory size is a per-device function attribute, so a process that drives several GPUs has to set it on
+// each of them (one process per GPU is the normal deployment, but nothing here relies on it).
+constexpr int kMaxCachedDevices = 64;
+struct LaunchConfig {
+    bool configured;
+    int blocks_per_sm;
+    int sms;
+};
+template <typename MainKernel, typename LongKernel>
+inline cudaError_t configure_pair(LaunchConfig &c, MainKernel main_kernel, LongKernel long_kernel, int main_threads,
+                                  size_t smem_main, size_t smem_long)
+{
+    cudaError_t err = cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main);
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long);
+    if (err != cudaSuccess) return err;
+    int blocks = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, main_kernel, main_threads, smem_main);
+    if (err != cudaSuccess) return err;
+    c.blocks_per_sm = blocks < 1 ? 1 : blocks;
+    c.sms = device_sm_count();
+    c.configured = true;
+    return cudaSuccess;
 }
 
 }  // namespace maxk

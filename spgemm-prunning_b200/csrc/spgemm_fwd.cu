@@ -218,7 +218,7 @@ __device__ __forceinline__ void write_row(float *acc, float *__restrict__ out_ro
     for (int i = 0; i < LY::kWords / 128; ++i) acc4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_div) {                                    // warp-uniform
         const float r = 1.0f / div;
-        if (r != 0.f && fabsf(r) <= 3.0e38f) {        // normal divisor (degrees are >= 1): reciprocal path
+        if (recip_usable(r)) {                        // normal divisor (degrees are >= 1): reciprocal path
 #pragma unroll
             for (int n = 0; n < kAccDim / 32; ++n) o[n] = div_by_recip(o[n], div, r);
         } else {                                      // zero / infinite / NaN divisor: plain IEEE division
@@ -339,10 +339,7 @@ spgemm_fwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict_
         __syncthreads();
         for (int i = threadIdx.x; i < kLongWarps * LY::kWords; i += kLongThreads) smem[i] = 0.f;
         if (threadIdx.x < dim) {
-            if (row_div != nullptr) {
-                const float d = row_div[r];
-                o = div_by_recip(o, d, 1.0f / d);
-            }
+            if (row_div != nullptr) o = div_guarded(o, row_div[r]);
             out[(size_t)r * dim + threadIdx.x] = o;
         }
     }
@@ -370,21 +367,21 @@ static cudaError_t launch_fwd(const int *row_begin, const int *row_end, const in
     using LY = Lay<K>;
     const size_t smem_main = (size_t)kFwdWarps * LY::kWords * sizeof(float);
     const size_t smem_long = (size_t)kLongWarps * LY::kWords * sizeof(float);
-    static bool configured = false;  // per template instance
-    static int blocks_per_sm = 1;
-    static int sms = kNumSMsB200;
-    if (!configured) {
-        cudaFuncSetAttribute(spgemm_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main);
-        cudaFuncSetAttribute(spgemm_fwd_long_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, spgemm_fwd_kernel<K>, kFwdThreads, smem_main);
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-        sms = device_sm_count();
-        configured = true;
-    }
-    int *long_rows = reinterpret_cast<int *>(ws + 1);
-    cudaError_t err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
+    static LaunchConfig cache[kMaxCachedDevices];  // per template instance and device
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
-    const int grid = sms * blocks_per_sm;
+    LaunchConfig uncached = {false, 1, kNumSMsB200};
+    LaunchConfig &cfg = (dev >= 0 && dev < kMaxCachedDevices) ? cache[dev] : uncached;
+    if (!cfg.configured) {
+        err = configure_pair(cfg, spgemm_fwd_kernel<K>, spgemm_fwd_long_kernel<K>, kFwdThreads, smem_main, smem_long);
+        if (err != cudaSuccess) return err;
+    }
+    const int sms = cfg.sms;
+    int *long_rows = reinterpret_cast<int *>(ws + 1);
+    err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
+    if (err != cudaSuccess) return err;
+    const int grid = sms * cfg.blocks_per_sm;
     const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kFwdWarps);
     spgemm_fwd_kernel<K><<<grid, kFwdThreads, smem_main, stream>>>(row_begin, row_end, idx, val, cval, csel, out,
                                                                    (int)n_rows, dim, k, row_div, ws, long_rows, rpg);

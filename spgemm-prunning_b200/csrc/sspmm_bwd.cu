@@ -49,7 +49,7 @@ __device__ __forceinline__ void stage_row(const float (&gv)[kAccDim / 32], float
     for (int n = 0; n < kAccDim / 32; ++n) a[n] = gv[n];
     if (has_div) {                                    // warp-uniform; one reciprocal per row (maxk_common.cuh)
         const float r = 1.0f / div;
-        if (r != 0.f && fabsf(r) <= 3.0e38f) {        // normal divisor (degrees are >= 1): reciprocal path
+        if (recip_usable(r)) {                        // normal divisor (degrees are >= 1): reciprocal path
 #pragma unroll
             for (int n = 0; n < kAccDim / 32; ++n) a[n] = div_by_recip(a[n], div, r);
         } else {                                      // zero / infinite / NaN divisor: plain IEEE division
@@ -285,25 +285,25 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
 {
     const size_t smem_main = (size_t)kBwdWarps * Lay<K>::kWords * sizeof(float);
     const size_t smem_long = (size_t)kBwdLongWarps * Lay<K>::kWords * sizeof(float);
-    static bool configured = false;
-    static int blocks_per_sm = 1;
-    static int sms = kNumSMsB200;
-    if (!configured) {
-        cudaFuncSetAttribute(sspmm_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main);
-        cudaFuncSetAttribute(sspmm_bwd_long_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sspmm_bwd_kernel<K>, kBwdThreads, smem_main);
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-        sms = device_sm_count();
-        configured = true;
+    static LaunchConfig cache[kMaxCachedDevices];  // per template instance and device
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    LaunchConfig uncached = {false, 1, kNumSMsB200};
+    LaunchConfig &cfg = (dev >= 0 && dev < kMaxCachedDevices) ? cache[dev] : uncached;
+    if (!cfg.configured) {
+        err = configure_pair(cfg, sspmm_bwd_kernel<K>, sspmm_bwd_long_kernel<K>, kBwdThreads, smem_main, smem_long);
+        if (err != cudaSuccess) return err;
     }
+    const int sms = cfg.sms;
     int *long_rows = reinterpret_cast<int *>(ws + 1);
-    cudaError_t err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
+    err = cudaMemsetAsync(ws, 0, sizeof(SchedWorkspace), stream);
     if (err != cudaSuccess) return err;
     if (zero_fill) {
         err = cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n_dst * k, stream);
         if (err != cudaSuccess) return err;
     }
-    const int grid = sms * blocks_per_sm;
+    const int grid = sms * cfg.blocks_per_sm;
     const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kBwdWarps);
     sspmm_bwd_kernel<K><<<grid, kBwdThreads, smem_main, stream>>>(row_begin, row_end, idx, val, g, csel, gs, (int)n_rows, dim,
                                                           k, row_div, ws, long_rows, rpg);
