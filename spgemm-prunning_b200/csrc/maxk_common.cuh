@@ -94,6 +94,13 @@ __device__ __forceinline__ float4 ld_stream_f32x4(const float *p)
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy_evict_first()));
     return v;
 }
+// 32 bytes per lane in one instruction (sm_100: LDG.E.256), 32-byte aligned address.
+__device__ __forceinline__ void ld_stream_f32x8(const float *p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p), "l"(policy_evict_first()));
+}
 // Re-used (gathered) operands: keep them in L2.
 __device__ __forceinline__ float4 ld_keep_f32x4(const float *p, uint64_t pol)
 {
@@ -128,6 +135,11 @@ __device__ __forceinline__ void st_stream_f32(float *p, float v)
 __device__ __forceinline__ void st_stream_f32x4(float *p, float4 v)
 {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_f32x8(float *p, const float (&v)[8])
+{
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 // 16-byte vector reduction into global memory (sm_90+): one L2 atomic per 4 floats.
 __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d, uint64_t pol)

@@ -43,12 +43,65 @@ __constant__ uint32_t c_recip31[kAccDim + 1] = {
 #include "recip31_table.inc"
 };
 
+// Warp-wide count of keys >= t.  Per lane it is 8 - #(key < t), read off the borrow of key - t: two IADD3
+// per key (carry-out, add-with-carry) where the compare / select / add the compiler emits for
+// `c += key >= t` is three; the search below is issue-bound, so this is a third off its inner loop.
+// One asm block: the condition code must not be live across separate asm statements.
 __device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
 {
-    int c = 0;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) c += (key[s] >= t) ? 1 : 0;
+    int c = 8;
+    asm("{\n\t.reg .u32 d;\n\t"
+        "sub.cc.u32 d, %1, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %2, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %3, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %4, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %5, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %6, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %7, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
+        "sub.cc.u32 d, %8, %9;\n\tsubc.s32 %0, %0, 0;\n\t}"
+        : "+r"(c)
+        : "r"(key[0]), "r"(key[1]), "r"(key[2]), "r"(key[3]), "r"(key[4]), "r"(key[5]), "r"(key[6]), "r"(key[7]), "r"(t));
     return __reduce_add_sync(kFullT, c);
+}
+
+// Threshold T with count(key > T) <= k <= count(key >= T), given a bracket: count(>= kmin) >= k and kmax
+// the largest key of the row.  Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots come
+// from linear interpolation of the count (few steps on smooth data) with a plain bisection step whenever
+// the same end moved twice in a row (guaranteed progress on anything); stops early when exactly k keys
+// are at or above the pivot (`exact`: no tie handling needed).
+__device__ __forceinline__ uint32_t find_threshold(const uint32_t (&key)[8], int k, uint32_t kmin, uint32_t kmax,
+                                                   bool &exact)
+{
+    exact = false;
+    if (kmax == 0xffffffffu && count_ge(key, kmax) >= k) return kmax;   // (NaN rows only) rank k lies inside the run of maximal keys
+    // hi is exclusive: nothing is >= kmax + 1 (kmax = 0xffffffff keeps hi = kmax, whose count is < k here)
+    uint32_t lo = kmin, hi = kmax == 0xffffffffu ? kmax : kmax + 1u;
+    int c_lo = count_ge(key, lo);
+    int c_hi = kmax == 0xffffffffu ? count_ge(key, kmax) : 0;
+    int side = 0, repeat = 0;            // which end moved last and how often in a row
+    exact = (c_lo == k);
+    while (!exact && hi - lo > 1u) {
+        const uint32_t span = hi - lo;
+        // secant step: off = span * (c_lo - k + 1/2) / (c_lo - c_hi) in integers; counts are <= 256
+        // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32); a bisection step
+        // whenever one end has been stuck twice in a row.  Selects, not branches: the loop body is
+        // straight-line code around one count.
+        const uint32_t num = (uint32_t)(2 * (c_lo - k) + 1);
+        const uint32_t sec = min(max(__umulhi(span, num * c_recip31[c_lo - c_hi]), 1u), span - 1u);
+        const bool bisect = repeat >= 2;
+        const uint32_t mid = lo + (bisect ? (span >> 1) : sec);
+        const int c = count_ge(key, mid);
+        const bool up = c >= k;                  // the lower end moves
+        const int moved = up ? 1 : 2;
+        repeat = (moved == side) ? (bisect ? 1 : repeat + 1) : 0;
+        side = moved;
+        lo = up ? mid : lo;
+        c_lo = up ? c : c_lo;
+        hi = up ? hi : mid;
+        c_hi = up ? c_hi : c;
+        exact = (c == k);
+    }
+    return lo;
 }
 
 // DIM256: dim == 256 (two 16-byte loads per lane, no padding logic).  ORDER: MAXK_ORDER_*.
@@ -113,43 +166,8 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
             kmin = __reduce_min_sync(kFullT, kmin);
         }
 
-        // ---- threshold T with count(key > T) <= k <= count(key >= T) -------------------------------
-        // Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots come from linear
-        // interpolation of the count (few steps on smooth data) with a plain bisection step whenever
-        // the same end moved twice in a row (guaranteed progress on anything); stops early when
-        // exactly k keys are at or above the pivot.
-        uint32_t T;
-        bool exact = false;                      // exactly k keys >= T: no tie handling needed
-        if (kmax == 0xffffffffu && count_ge(key, kmax) >= k) {
-            T = kmax;                            // (NaN rows only) rank k lies inside the run of maximal keys
-        } else {
-            // hi is exclusive: nothing is >= kmax + 1 (kmax = 0xffffffff keeps hi = kmax, whose count is < k here)
-            uint32_t lo = kmin, hi = kmax == 0xffffffffu ? kmax : kmax + 1u;
-            int c_lo = count_ge(key, lo);
-            int c_hi = kmax == 0xffffffffu ? count_ge(key, kmax) : 0;
-            int side = 0, repeat = 0;            // which end moved last and how often in a row
-            exact = (c_lo == k);
-            while (!exact && hi - lo > 1u) {
-                const uint32_t span = hi - lo;
-                uint32_t mid = lo + (span >> 1);
-                if (repeat < 2) {                // secant step; a bisection step whenever one end is stuck
-                    // off = span * (c_lo - k + 1/2) / (c_lo - c_hi) in integers: counts are <= 256
-                    // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32)
-                    const uint32_t num = (uint32_t)(2 * (c_lo - k) + 1);
-                    const uint32_t off = __umulhi(span, num * c_recip31[c_lo - c_hi]);
-                    mid = lo + min(max(off, 1u), span - 1u);
-                } else {
-                    repeat = 0;
-                }
-                const int c = count_ge(key, mid);
-                const int moved = c >= k ? 1 : 2;
-                repeat = moved == side ? repeat + 1 : 0;
-                side = moved;
-                if (c >= k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
-                if (c == k) exact = true;
-            }
-            T = lo;
-        }
+        bool exact;
+        const uint32_t T = find_threshold(key, k, kmin, kmax, exact);
 
         // ---- selection flags ---------------------------------------------------------------------
         bool selb[8];
@@ -281,6 +299,138 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The layer's hot configuration: dim == 256, MAXK_ORDER_BANKED, k in {8, 16, 32, 64}.
+//
+// Same selection as the general kernel above, arranged for the fewest issued instructions (the general
+// kernel issues ~565 warp instructions per row and is issue-bound at 78 % of the issue slots, 19 % of
+// HBM bandwidth): lane l owns the 8 CONSECUTIVE columns 8l .. 8l+7 (one 32-byte load per lane), so
+// that a column's bank-residue class mod 8 is its register slot and the banked output position of an
+// entry is a prefix over the slots' ballots instead of a lane-group exchange; (value, column) pairs are
+// staged as one 8-byte shared-memory store; k is a template parameter.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kTopkThreads)
+topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restrict__ out_val,
+                   uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32, int64_t *__restrict__ out_i64,
+                   float *__restrict__ masked)
+{
+    constexpr int M = K == 64 ? 16 : K == 32 ? 8 : 4;       // banked_modulus(K)
+    __shared__ __align__(8) uint32_t s_ent[kTopkWarps][2 * K];   // (value bits, column id) pairs
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
+    const unsigned lt = (1u << lane) - 1u;
+
+    for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
+        float v[8];
+        ld_stream_f32x8(x + r * kAccDim + 8 * lane, v);
+        uint32_t key[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) key[s] = fast_key(v[s]);
+        // bracket: lo = min over lanes of the lane's ceil(K/32)-th largest key (see the general kernel)
+        uint32_t m1 = max(key[0], key[1]), m2 = min(key[0], key[1]);
+#pragma unroll
+        for (int s = 2; s < 8; ++s) {
+            if (K > 32) m2 = max(m2, min(m1, key[s]));
+            m1 = max(m1, key[s]);
+        }
+        const uint32_t kmax = __reduce_max_sync(kFullT, m1);
+        const uint32_t kmin = __reduce_min_sync(kFullT, K > 32 ? m2 : m1);
+        bool exact;
+        const uint32_t T = find_threshold(key, K, kmin, kmax, exact);
+
+        bool selb[8];
+        if (exact) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) selb[s] = key[s] >= T;
+        } else {
+            // ties straddle rank K: key > T always, key == T lowest column first = (lane, slot) order
+            int gt_total = 0, rk = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                gt_total += __popc(__ballot_sync(kFullT, key[s] > T));
+                rk += __popc(__ballot_sync(kFullT, key[s] == T) & lt);
+            }
+            const int need_eq = K - gt_total;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const bool is_eq = key[s] == T;
+                selb[s] = (key[s] > T) || (is_eq && rk < need_eq);
+                rk += is_eq ? 1 : 0;
+            }
+        }
+
+        if (masked != nullptr) {
+            float mv[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) mv[s] = selb[s] ? v[s] : 0.f;
+            st_stream_f32x8(masked + r * kAccDim + 8 * lane, mv);
+        }
+
+        // ---- banked output positions: class = column mod M, columns ascending inside a class -------------
+        unsigned bs[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) bs[s] = __ballot_sync(kFullT, selb[s]);
+        int pos[8];
+        if (M == 8) {                    // class == slot
+            int base = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                pos[s] = base + __popc(bs[s] & lt);
+                base += __popc(bs[s]);
+            }
+        } else if (M == 4) {             // class == slot & 3; inside a class: (lane, slot < 4 first)
+            int base = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pos[u] = base + __popc(bs[u] & lt) + __popc(bs[u + 4] & lt);
+                pos[u + 4] = pos[u] + (selb[u] ? 1 : 0);
+                base += __popc(bs[u]) + __popc(bs[u + 4]);
+            }
+        } else {                         // M == 16: class == 8 * (lane & 1) + slot
+            const unsigned pm = (lane & 1) ? 0xaaaaaaaau : 0x55555555u;   // lanes of my parity
+            int mine[8], total = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                mine[s] = __popc(bs[s] & pm);
+                total += mine[s];
+            }
+            int base = (lane & 1) ? K - total : 0;    // exactly K entries are selected: the even lanes hold K - odd
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                pos[s] = base + __popc(bs[s] & pm & lt);
+                base += mine[s];
+            }
+        }
+
+        // ---- stage the K entries in shared memory, then coalesced stores --------------------------------
+        uint32_t *ent_w = s_ent[warp];
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (selb[s]) {                    // two 4-byte stores off one address (an 8-byte store needs a register pair)
+                uint32_t *e = ent_w + 2 * pos[s];
+                e[0] = __float_as_uint(v[s]);
+                e[1] = (uint32_t)(8 * lane + s);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int i0 = 0; i0 < K; i0 += 32) {
+            const int i = i0 + lane;
+            if (K >= 32 || i < K) {
+                const uint2 ent = *reinterpret_cast<const uint2 *>(ent_w + 2 * i);
+                const int c = (int)ent.y;
+                const int64_t o = r * K + i;
+                out_val[o] = __uint_as_float(ent.x);
+                if (out_sel) out_sel[o] = (uint8_t)c;
+                if (out_i32) out_i32[o] = c;
+                if (out_i64) out_i64[o] = c;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // dense[r, sel[r,l]] = vals[r,l], everything else 0 (one warp per row, row written once).
 __global__ void __launch_bounds__(kTopkThreads)
 cbsr_scatter_kernel(const float *__restrict__ vals, const uint8_t *__restrict__ sel, int64_t n_rows, int dim, int k,
@@ -370,6 +520,30 @@ dense_spmm_kernel(const int *__restrict__ indptr, const int *__restrict__ idx, c
     }
 }
 
+// One resident wave: the grid is what the device holds at once (cached per device), rows beyond it are
+// taken by the grid-stride loop, so that no SM idles while a partial second wave drains.
+template <int K>
+static cudaError_t launch_topk_banked(const float *x, int64_t n_rows, float *cbsr_val, uint8_t *cbsr_sel,
+                                      int32_t *idx_i32, int64_t *idx_i64, float *masked, cudaStream_t st)
+{
+    static int resident[kMaxCachedDevices];    // CTAs per device, 0 = not queried yet
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    int local = 0;
+    int &cap = (dev >= 0 && dev < kMaxCachedDevices) ? resident[dev] : local;
+    if (cap == 0) {
+        int per_sm = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_banked_kernel<K>, kTopkThreads, 0);
+        if (err != cudaSuccess) return err;
+        cap = device_sm_count() * (per_sm < 1 ? 1 : per_sm);
+    }
+    const int64_t need = (n_rows + kTopkWarps - 1) / kTopkWarps;
+    const int grid = (int)(need < cap ? need : cap);
+    topk_banked_kernel<K><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked);
+    return cudaGetLastError();
+}
+
 static int grid_for_rows(int64_t n_rows)
 {
     int dev = 0, sms = kNumSMsB200;
@@ -401,6 +575,17 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     const int grid = grid_for_rows(n_rows);
     const int bm = banked_modulus(k);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dim == kAccDim && order == MAXK_ORDER_BANKED && bm >= 4 && !(((uintptr_t)x | (uintptr_t)masked) & 31)) {
+        // the layer's hot configurations (32-byte loads need 32-byte aligned rows)
+        cudaError_t err;
+        switch (k) {
+            case 8: err = launch_topk_banked<8>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+            case 16: err = launch_topk_banked<16>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+            case 32: err = launch_topk_banked<32>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+            default: err = launch_topk_banked<64>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+        }
+        return status_from_cuda(err);
+    }
 #define MAXK_TOPK_LAUNCH(D256, ORD) \
     topk_cbsr_kernel<D256, ORD><<<grid, kTopkThreads, 0, st>>>(x, n_rows, dim, k, bm, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked)
     if (dim == kAccDim) {
