@@ -43,24 +43,27 @@ __constant__ uint32_t c_recip31[kAccDim + 1] = {
 #include "recip31_table.inc"
 };
 
-// Warp-wide count of keys >= t.  Per lane it is 8 - #(key < t), read off the borrow of key - t: two IADD3
-// per key (carry-out, add-with-carry) where the compare / select / add the compiler emits for
-// `c += key >= t` is three; the search below is issue-bound, so this is a third off its inner loop.
-// One asm block: the condition code must not be live across separate asm statements.
-__device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
+// Warp-wide count of keys >= t.  The search is bound by the ALU pipe (ncu: 75 % of its peak, one warp
+// instruction per two cycles; the FMA pipe 17 %), so the count is split over both pipes: the compare is an
+// ALU-pipe ISETP, the increment a predicated IMAD c = one * one + c on the FMA pipe.  `one` is a kernel
+// argument holding 1 -- with a literal the compiler folds the multiply into an ALU-pipe add again
+// (tools/count_bench.cu: 30 cycles per count per scheduler against 39 for what `c += key >= t` compiles to
+// and 43 for a borrow chain of IADD3 pairs).
+__device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t, int one)
 {
-    int c = 8;
-    asm("{\n\t.reg .u32 d;\n\t"
-        "sub.cc.u32 d, %1, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %2, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %3, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %4, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %5, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %6, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %7, %9;\n\tsubc.s32 %0, %0, 0;\n\t"
-        "sub.cc.u32 d, %8, %9;\n\tsubc.s32 %0, %0, 0;\n\t}"
+    int c = 0;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.u32 p, %1, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %2, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %3, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %4, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %5, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %6, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %7, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t"
+        "setp.ge.u32 p, %8, %9;\n\t@p mad.lo.s32 %0, %10, %10, %0;\n\t}"
         : "+r"(c)
-        : "r"(key[0]), "r"(key[1]), "r"(key[2]), "r"(key[3]), "r"(key[4]), "r"(key[5]), "r"(key[6]), "r"(key[7]), "r"(t));
+        : "r"(key[0]), "r"(key[1]), "r"(key[2]), "r"(key[3]), "r"(key[4]), "r"(key[5]), "r"(key[6]), "r"(key[7]), "r"(t),
+          "r"(one));
     return __reduce_add_sync(kFullT, c);
 }
 
@@ -70,14 +73,14 @@ __device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t)
 // the same end moved twice in a row (guaranteed progress on anything); stops early when exactly k keys
 // are at or above the pivot (`exact`: no tie handling needed).
 __device__ __forceinline__ uint32_t find_threshold(const uint32_t (&key)[8], int k, uint32_t kmin, uint32_t kmax,
-                                                   bool &exact)
+                                                   bool &exact, int one)
 {
     exact = false;
-    if (kmax == 0xffffffffu && count_ge(key, kmax) >= k) return kmax;   // (NaN rows only) rank k lies inside the run of maximal keys
+    if (kmax == 0xffffffffu && count_ge(key, kmax, one) >= k) return kmax;   // (NaN rows only) rank k lies inside the run of maximal keys
     // hi is exclusive: nothing is >= kmax + 1 (kmax = 0xffffffff keeps hi = kmax, whose count is < k here)
     uint32_t lo = kmin, hi = kmax == 0xffffffffu ? kmax : kmax + 1u;
-    int c_lo = count_ge(key, lo);
-    int c_hi = kmax == 0xffffffffu ? count_ge(key, kmax) : 0;
+    int c_lo = count_ge(key, lo, one);
+    int c_hi = kmax == 0xffffffffu ? count_ge(key, kmax, one) : 0;
     int side = 0, repeat = 0;            // which end moved last and how often in a row
     exact = (c_lo == k);
     while (!exact && hi - lo > 1u) {
@@ -90,7 +93,7 @@ __device__ __forceinline__ uint32_t find_threshold(const uint32_t (&key)[8], int
         const uint32_t sec = min(max(__umulhi(span, num * c_recip31[c_lo - c_hi]), 1u), span - 1u);
         const bool bisect = repeat >= 2;
         const uint32_t mid = lo + (bisect ? (span >> 1) : sec);
-        const int c = count_ge(key, mid);
+        const int c = count_ge(key, mid, one);
         const bool up = c >= k;                  // the lower end moves
         const int moved = up ? 1 : 2;
         repeat = (moved == side) ? (bisect ? 1 : repeat + 1) : 0;
@@ -109,7 +112,7 @@ template <bool DIM256, int ORDER>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, int bank_mod,
                  float *__restrict__ out_val, uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32,
-                 int64_t *__restrict__ out_i64, float *__restrict__ masked)
+                 int64_t *__restrict__ out_i64, float *__restrict__ masked, int one)
 {
     __shared__ float s_val[kTopkWarps][kAccDim];
     __shared__ uint8_t s_col[kTopkWarps][kAccDim];
@@ -167,7 +170,7 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         }
 
         bool exact;
-        const uint32_t T = find_threshold(key, k, kmin, kmax, exact);
+        const uint32_t T = find_threshold(key, k, kmin, kmax, exact, one);
 
         // ---- selection flags ---------------------------------------------------------------------
         bool selb[8];
@@ -313,7 +316,7 @@ template <int K>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restrict__ out_val,
                    uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32, int64_t *__restrict__ out_i64,
-                   float *__restrict__ masked)
+                   float *__restrict__ masked, int one)
 {
     constexpr int M = K == 64 ? 16 : K == 32 ? 8 : 4;       // banked_modulus(K)
     __shared__ __align__(8) uint32_t s_ent[kTopkWarps][2 * K];   // (value bits, column id) pairs
@@ -322,9 +325,17 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
     const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
     const unsigned lt = (1u << lane) - 1u;
 
-    for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
+    // The next row of the warp is loaded while the current one is searched: a warp that only loads between
+    // rows keeps ~1/3 of its 1 KiB in flight on average, and 40 warps x 1/3 KiB per SM is far below the
+    // ~44 KiB per SM that the HBM latency-bandwidth product asks for (measured: 1.7-2.0 TB/s without).
+    int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp;
+    float nv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < n_rows) ld_stream_f32x8(x + r * kAccDim + 8 * lane, nv);
+    for (; r < n_rows; r += warps_total) {
         float v[8];
-        ld_stream_f32x8(x + r * kAccDim + 8 * lane, v);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v[s] = nv[s];
+        if (r + warps_total < n_rows) ld_stream_f32x8(x + (r + warps_total) * kAccDim + 8 * lane, nv);
         uint32_t key[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) key[s] = fast_key(v[s]);
@@ -338,7 +349,7 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
         const uint32_t kmax = __reduce_max_sync(kFullT, m1);
         const uint32_t kmin = __reduce_min_sync(kFullT, K > 32 ? m2 : m1);
         bool exact;
-        const uint32_t T = find_threshold(key, K, kmin, kmax, exact);
+        const uint32_t T = find_threshold(key, K, kmin, kmax, exact, one);
 
         bool selb[8];
         if (exact) {
@@ -540,7 +551,7 @@ static cudaError_t launch_topk_banked(const float *x, int64_t n_rows, float *cbs
     }
     const int64_t need = (n_rows + kTopkWarps - 1) / kTopkWarps;
     const int grid = (int)(need < cap ? need : cap);
-    topk_banked_kernel<K><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked);
+    topk_banked_kernel<K><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1);
     return cudaGetLastError();
 }
 
@@ -587,7 +598,7 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
         return status_from_cuda(err);
     }
 #define MAXK_TOPK_LAUNCH(D256, ORD) \
-    topk_cbsr_kernel<D256, ORD><<<grid, kTopkThreads, 0, st>>>(x, n_rows, dim, k, bm, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked)
+    topk_cbsr_kernel<D256, ORD><<<grid, kTopkThreads, 0, st>>>(x, n_rows, dim, k, bm, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1)
     if (dim == kAccDim) {
         if (order == MAXK_ORDER_VALUE_DESC) MAXK_TOPK_LAUNCH(true, MAXK_ORDER_VALUE_DESC);
         else if (order == MAXK_ORDER_COLUMN_ASC || bm < 4) MAXK_TOPK_LAUNCH(true, MAXK_ORDER_COLUMN_ASC);
