@@ -174,7 +174,7 @@ def workload_config(args, n, e):
                         "hidden %d, k=%d: top-k + fwd SpGEMM + bwd SSpMM" % (args.shape, n, e, DIM, args.k),
             "shape": args.shape, "nodes": n, "edges": e, "hidden": DIM, "k": args.k,
             "l2_note": "inputs per step (CSR 917 MB + features 239 MB + gradient 239 MB) exceed the 126 MB L2; no flush needed",
-            "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs, all_gather(CBSR) fwd, %s bwd" % (args.gpus, args.bwd_mode)}
+            "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs (%s partition), all_gather(CBSR) fwd, %s bwd" % (args.gpus, "equal-row" if args.partition == "rows" else "equal-edge", args.bwd_mode)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -272,9 +272,9 @@ def run_ours(args, n, e):
         roof_bytes, roof_ms = b_fwd, t_fwd
         scaling = "strong"
     else:
-        from sharded import ShardedMaxKAggregation, slab_rows
-        layer = ShardedMaxKAggregation(graph, k, backward_mode=args.bwd_mode)
-        m = slab_rows(n, world)
+        from sharded import ShardedMaxKAggregation
+        layer = ShardedMaxKAggregation(graph, k, backward_mode=args.bwd_mode, partition=args.partition)
+        m = layer.m
         x = torch.rand(m, DIM, device=dev, generator=gen)
         grad = torch.rand(m, DIM, device=dev, generator=gen)
         del graph
@@ -381,6 +381,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bwd-mode", default="reduce_scatter", choices=["reduce_scatter", "allgather", "overlap"],
                     help="multi-GPU backward exchange (sharded.py)")
+    ap.add_argument("--partition", default="rows", choices=["rows", "nnz"],
+                    help="multi-GPU row partition: equal row slabs, or equal edge counts (identical on the uniform contract graph)")
     args = ap.parse_args()
     from synth_graphs import SHAPES
     n, e = SHAPES[args.shape]

@@ -48,33 +48,72 @@ def row_bounds(n, world, rank):
     return lo, min(lo + m, n)
 
 
-def shard_rows(graph, world, rank):
-    """Row slab of a CSR graph: local indptr (rebased, padded to m rows), global column ids."""
-    n = graph["v_num"]
+def uniform_bounds(n, world):
+    """Slab boundaries [b_0 .. b_P] of the equal-row partition."""
     m = slab_rows(n, world)
-    lo, hi = row_bounds(n, world, rank)
+    return [min(p * m, n) for p in range(world + 1)]
+
+
+def balanced_bounds(indptr, world):
+    """Slab boundaries with ~E/P edges per rank (prefix sum of the degrees): rank p owns rows
+    [b_p, b_p+1).  Equal-row slabs put E/P edges on every rank only on uniform graphs; on a power-law
+    graph the rank that holds the hubs sets the step time."""
+    indptr = torch.as_tensor(indptr).long().cpu()
+    n, e = indptr.numel() - 1, int(indptr[-1])
+    targets = torch.tensor([(p * e) // world for p in range(1, world)], dtype=torch.int64)
+    cuts = torch.searchsorted(indptr, targets, right=False).clamp(max=n).tolist() if world > 1 else []
+    bounds = [0] + cuts + [n]
+    for p in range(1, len(bounds)):                   # monotone (empty slabs are legal)
+        bounds[p] = max(bounds[p], bounds[p - 1])
+    return bounds
+
+
+def padded_position(ids, bounds, m):
+    """Position of global row / column ids in the padded numbering owner * m + (id - b_owner), the layout
+    of every all_gathered [P * m, ...] buffer.  Identity for the equal-row partition."""
+    b = torch.as_tensor(bounds[:-1], dtype=torch.int64, device=ids.device)
+    ids = ids.long()
+    owner = torch.searchsorted(b, ids, right=True) - 1
+    # rows of empty slabs share a boundary: searchsorted(right=True) picks the last slab starting there,
+    # which is the one that owns the row
+    return owner * m + (ids - b[owner])
+
+
+def shard_rows(graph, world, rank, bounds=None):
+    """Row slab of a CSR graph: local indptr (rebased, padded to m rows), column ids in the padded global
+    numbering (== global ids for the equal-row partition)."""
+    n = graph["v_num"]
+    uniform = bounds is None
+    if uniform:
+        bounds = uniform_bounds(n, world)
+    m = max(1, max(bounds[p + 1] - bounds[p] for p in range(world)))
+    lo, hi = bounds[rank], bounds[rank + 1]
     indptr = graph["indptr"]
     e0, e1 = int(indptr[lo]), int(indptr[hi])
     local_ptr = torch.full((m + 1,), e1 - e0, dtype=torch.int32, device=indptr.device)
     local_ptr[: hi - lo + 1] = indptr[lo:hi + 1] - e0
-    return {"indptr": local_ptr, "indices": graph["indices"][e0:e1].contiguous(),
+    indices = graph["indices"][e0:e1]
+    if not uniform:
+        indices = padded_position(indices, bounds, m).to(torch.int32)
+    return {"indptr": local_ptr, "indices": indices.contiguous(),
             "values": graph["values"][e0:e1].contiguous(), "v_num": m, "e_num": e1 - e0,
             "n_global": n, "row_lo": lo, "row_hi": hi}
 
 
-def shard_columns(graph, world, rank):
-    """Column slab A[:, rows_p] as a CSR over ALL n source rows (padded to P*m), local column ids.
-    Used by the all_gather backward variant."""
+def shard_columns(graph, world, rank, bounds=None):
+    """Column slab A[:, rows_p] as a CSR over ALL source rows in the padded numbering (P*m rows), local
+    column ids.  Used by the all_gather backward variant."""
     n = graph["v_num"]
-    m = slab_rows(n, world)
-    lo, hi = row_bounds(n, world, rank)
+    if bounds is None:
+        bounds = uniform_bounds(n, world)
+    m = max(1, max(bounds[p + 1] - bounds[p] for p in range(world)))
+    lo, hi = bounds[rank], bounds[rank + 1]
     indptr, indices, values = graph["indptr"].long(), graph["indices"], graph["values"]
     keep = (indices >= lo) & (indices < hi)
     rows = torch.repeat_interleave(torch.arange(n, device=indices.device), indptr[1:] - indptr[:-1])
-    counts = torch.bincount(rows[keep], minlength=n)
+    counts = torch.bincount(padded_position(rows[keep], bounds, m), minlength=world * m)
     ptr = torch.zeros(world * m + 1, dtype=torch.int64, device=indices.device)
-    ptr[1:n + 1] = torch.cumsum(counts, 0)
-    ptr[n + 1:] = ptr[n]
+    ptr[1:] = torch.cumsum(counts, 0)
     return {"indptr": ptr.to(torch.int32), "indices": (indices[keep] - lo).to(torch.int32).contiguous(),
             "values": values[keep].contiguous(), "v_num": world * m, "e_num": int(keep.sum())}
 
@@ -164,17 +203,23 @@ class ShardedMaxKAggregation:
     """top-k -> all_gather(CBSR) -> SpGEMM, and its backward, for one rank's row slab."""
 
     def __init__(self, graph, k, group=None, backward_mode="reduce_scatter", compute=None, row_div=None,
-                 overlap_chunks=4):
+                 overlap_chunks=4, partition="rows"):
         if backward_mode not in ("reduce_scatter", "allgather", "overlap"):
             raise ValueError("backward_mode must be 'reduce_scatter', 'allgather' or 'overlap'")
+        if partition not in ("rows", "nnz"):
+            raise ValueError("partition must be 'rows' (equal row slabs) or 'nnz' (equal edge counts)")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.k = int(k)
         self.n = graph["v_num"]
-        self.m = slab_rows(self.n, self.world)
-        self.rows = shard_rows(graph, self.world, self.rank)
-        self.cols = shard_columns(graph, self.world, self.rank) if backward_mode == "allgather" else None
+        self.partition = partition
+        # every rank derives the same boundaries from the same indptr: nothing is exchanged
+        self.bounds = uniform_bounds(self.n, self.world) if partition == "rows" else balanced_bounds(graph["indptr"], self.world)
+        explicit = None if partition == "rows" else self.bounds
+        self.rows = shard_rows(graph, self.world, self.rank, explicit)
+        self.m = self.rows["v_num"]                   # padded slab height, the same on every rank
+        self.cols = shard_columns(graph, self.world, self.rank, explicit) if backward_mode == "allgather" else None
         self.backward_mode = backward_mode
         self.compute = compute if compute is not None else CudaCompute()
         self.row_div = None
@@ -195,7 +240,18 @@ class ShardedMaxKAggregation:
                 self.chunks = [{"owners": o, "begin": pos[c], "end": pos[c + 1]} for c, o in enumerate(owners)]
                 self.comm_stream = torch.cuda.Stream() if self.rows["indices"].is_cuda else None
 
-    # x_local: [m, 256] (rows past the end of the graph are padding and may hold anything finite)
+    def local_slab(self, full):
+        """This rank's rows of a full [N, ...] tensor, zero-padded to the slab height m."""
+        lo, hi = self.rows["row_lo"], self.rows["row_hi"]
+        out = full.new_zeros((self.m,) + tuple(full.shape[1:]))
+        out[: hi - lo] = full[lo:hi]
+        return out
+
+    def valid_rows(self):
+        """Number of real (non-padding) rows of this rank's slab."""
+        return self.rows["row_hi"] - self.rows["row_lo"]
+
+    # x_local: [m, 256] (rows past the end of the slab are padding and may hold anything finite)
     def forward(self, x_local):
         vals, sel = self.compute.topk(x_local, self.k)
         vals_full, self.sel_full = _all_gather_pair(vals, sel, self.group)
@@ -300,12 +356,12 @@ def sharded_maxk_spgemm(x_local, layer):
 # ------------------------------------------------------------------------------------------------
 class ShardedMaxKSAGE(torch.nn.Module):
     def __init__(self, graph, in_size, hid_size, num_hid_layers, out_size, maxk=32, feat_drop=0.0, norm=False,
-                 group=None, compute=None, backward_mode="reduce_scatter"):
+                 group=None, compute=None, backward_mode="reduce_scatter", partition="rows"):
         super().__init__()
         nn = torch.nn
         deg = torch.clamp((graph["indptr"][1:] - graph["indptr"][:-1]).to(torch.float32), min=1.0)
         self.agg = ShardedMaxKAggregation(graph, maxk, group=group, backward_mode=backward_mode, compute=compute,
-                                          row_div=deg)
+                                          row_div=deg, partition=partition)
         self.group = group
         self.fc_self = nn.ModuleList(nn.Linear(hid_size, hid_size) for _ in range(num_hid_layers))
         self.fc_neigh = nn.ModuleList(nn.Linear(hid_size, hid_size, bias=False) for _ in range(num_hid_layers))

@@ -17,7 +17,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from sharded import ShardedMaxKSAGE, allreduce_gradients, slab_rows
+from sharded import ShardedMaxKSAGE, allreduce_gradients
 from synth_graphs import SHAPES, symmetrize, synth_graph
 
 
@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--warmup_epochs", type=int, default=5)
     ap.add_argument("--bwd-mode", default="reduce_scatter")
+    ap.add_argument("--partition", default="nnz", choices=["rows", "nnz"],
+                    help="row partition: equal row slabs or equal edge counts (the graph here has power-law degrees)")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -43,15 +45,14 @@ def main():
     n, e = max(64, int(n * a.scale)), max(64, int(e * a.scale))
     graph = symmetrize(synth_graph(n, max(e // 2, 1), seed=123, kind="powerlaw", device=dev))   # same graph on every rank
     n = graph["v_num"]
-    m = slab_rows(n, world)
-    lo, hi = min(rank * m, n), min(rank * m + m, n)
+    torch.manual_seed(0)                                                # identical initial weights on every rank
+    model = ShardedMaxKSAGE(graph, a.in_size, a.hidden_dim, a.hidden_layers, a.classes, maxk=a.maxk,
+                            backward_mode=a.bwd_mode, partition=a.partition).to(dev)
+    m = model.agg.m                                                     # padded slab height (same on every rank)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn(m, a.in_size, device=dev, generator=gen)
     y = torch.randint(0, a.classes, (m,), device=dev, generator=gen)
-    valid = torch.arange(m, device=dev) < (hi - lo)
-    torch.manual_seed(0)                                                # identical initial weights on every rank
-    model = ShardedMaxKSAGE(graph, a.in_size, a.hidden_dim, a.hidden_layers, a.classes, maxk=a.maxk,
-                            backward_mode=a.bwd_mode).to(dev)
+    valid = torch.arange(m, device=dev) < model.agg.valid_rows()
     del graph
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
     fwd_ms = bwd_ms = 0.0

@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 import oracle
 from helpers import assert_close
-from sharded import ShardedMaxKAggregation, sharded_maxk_spgemm, slab_rows
+from sharded import ShardedMaxKAggregation, sharded_maxk_spgemm
 from synth_graphs import synth_graph
 
 pytestmark = pytest.mark.gpu
@@ -39,26 +39,23 @@ def _expected(g, x, grad, deg, k):
     return out, gs, oracle.scatter_dense(gs, cols)
 
 
-def _run_rank(rank, world, port, mode, result_dir):
+def _run_rank(rank, world, port, mode, result_dir, partition="rows"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         g, x, grad, deg, k = _problem()
         gc = {key: (v.cuda() if isinstance(v, torch.Tensor) else v) for key, v in g.items()}
-        n, m = g["v_num"], slab_rows(g["v_num"], world)
-        layer = ShardedMaxKAggregation(gc, k, backward_mode=mode, row_div=deg.cuda())   # default compute = CUDA kernels
-        lo = rank * m
-        rows = max(0, min(n, lo + m) - lo)
-        x_local, g_local = torch.zeros(m, 256, device="cuda"), torch.zeros(m, 256, device="cuda")
-        x_local[:rows], g_local[:rows] = x[lo:lo + rows].cuda(), grad[lo:lo + rows].cuda()
+        layer = ShardedMaxKAggregation(gc, k, backward_mode=mode, row_div=deg.cuda(),
+                                       partition=partition)                             # default compute = CUDA kernels
+        x_local, g_local = layer.local_slab(x.cuda()), layer.local_slab(grad.cuda())
         xl = x_local.clone().requires_grad_(True)
         out = sharded_maxk_spgemm(xl, layer)
         out.backward(g_local)
         gs = layer.backward(g_local)
         torch.cuda.synchronize()
         np.savez(os.path.join(result_dir, "rank%d.npz" % rank), out=out.detach().cpu().numpy(), gs=gs.cpu().numpy(),
-                 xgrad=xl.grad.cpu().numpy())
+                 xgrad=xl.grad.cpu().numpy(), lo=layer.rows["row_lo"], hi=layer.rows["row_hi"], edges=layer.rows["e_num"])
     finally:
         dist.destroy_process_group()
 
@@ -66,10 +63,9 @@ def _run_rank(rank, world, port, mode, result_dir):
 def _check(tmp_path, world):
     g, x, grad, deg, k = _problem()
     exp_out, exp_gs, exp_xgrad = _expected(g, x, grad, deg, k)
-    n, m = g["v_num"], slab_rows(g["v_num"], world)
     for rank in range(world):
         r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
-        lo, hi = rank * m, min(n, rank * m + m)
+        lo, hi = int(r["lo"]), int(r["hi"])
         assert_close(r["out"][: hi - lo], exp_out[lo:hi], "rank %d forward" % rank)
         assert_close(r["gs"][: hi - lo], exp_gs[lo:hi], "rank %d backward" % rank, rtol=2e-5)
         assert_close(r["xgrad"][: hi - lo], exp_xgrad[lo:hi], "rank %d autograd" % rank, rtol=2e-5)
@@ -87,3 +83,15 @@ def test_world2_nccl(tmp_path, mode):
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     mp.spawn(_run_rank, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
     _check(tmp_path, 2)
+
+
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather"])
+def test_world2_nccl_edge_balanced_partition(tmp_path, mode):
+    """partition="nnz" on a power-law graph: same results, and the two ranks hold (almost) the same number of edges."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    mp.spawn(_run_rank, args=(2, _free_port(), mode, str(tmp_path), "nnz"), nprocs=2, join=True)
+    _check(tmp_path, 2)
+    e = [int(np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))["edges"]) for r in range(2)]
+    g = _problem()[0]
+    assert sum(e) == g["e_num"] and abs(e[0] - e[1]) <= int((g["indptr"][1:] - g["indptr"][:-1]).max())

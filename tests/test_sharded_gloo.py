@@ -59,23 +59,21 @@ def _problem(n=203, e=4000, k=16):
     return g, x, grad, deg, k
 
 
-def _worker(rank, world, port, mode, use_div, result_dir):
+def _worker(rank, world, port, mode, use_div, result_dir, partition="rows"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g, x, grad, deg, k = _problem()
-        n, m = g["v_num"], slab_rows(g["v_num"], world)
-        layer = ShardedMaxKAggregation(g, k, backward_mode=mode, compute=OracleCompute(), row_div=deg if use_div else None)
-        lo = rank * m
-        x_local, g_local = torch.zeros(m, 256), torch.zeros(m, 256)
-        rows = max(0, min(n, lo + m) - lo)
-        x_local[:rows], g_local[:rows] = x[lo:lo + rows], grad[lo:lo + rows]
+        layer = ShardedMaxKAggregation(g, k, backward_mode=mode, compute=OracleCompute(), row_div=deg if use_div else None,
+                                       partition=partition)
+        x_local, g_local = layer.local_slab(x), layer.local_slab(grad)
         xl = x_local.clone().requires_grad_(True)
         out = sharded_maxk_spgemm(xl, layer)
         out.backward(g_local)
         gs = layer.backward(g_local)
         np.savez(os.path.join(result_dir, "rank%d.npz" % rank), out=out.detach().numpy(), gs=gs.numpy(),
-                 xgrad=xl.grad.numpy(), wire_fwd=layer.wire_bytes()["forward"], wire_bwd=layer.wire_bytes()["backward"])
+                 xgrad=xl.grad.numpy(), wire_fwd=layer.wire_bytes()["forward"], wire_bwd=layer.wire_bytes()["backward"],
+                 lo=layer.rows["row_lo"], hi=layer.rows["row_hi"], m=layer.m, edges=layer.rows["e_num"])
     finally:
         dist.destroy_process_group()
 
@@ -102,6 +100,61 @@ def test_sharded_layer_matches_single_process_oracle(tmp_path, mode, use_div):
         assert_close(r["xgrad"][: hi - lo], exp_xgrad[lo:hi], "rank %d autograd" % rank)
         assert int(r["wire_fwd"]) == m * k * 5
         assert int(r["wire_bwd"]) == (m * 256 * 4 if mode == "allgather" else m * k * 4)
+
+
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather", "overlap"])
+def test_edge_balanced_partition_matches_single_process_oracle(tmp_path, mode):
+    """partition="nnz": slab boundaries from the prefix sum of the degrees, slabs padded to a common height,
+    column ids remapped into the padded numbering -- same results as the single-process oracle, and the
+    edge counts of the two ranks differ by less than one hub row."""
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), mode, True, str(tmp_path), "nnz"), nprocs=world, join=True)
+    g, x, grad, deg, k = _problem()
+    ip, ix, va = (g[t].numpy() for t in ("indptr", "indices", "values"))
+    vals, cols = oracle.topk(x.numpy(), k, 2)
+    sel = cols.astype(np.uint8)
+    exp_out = oracle.spgemm_fwd(ip, ix, va, vals, sel, deg=deg.numpy())
+    exp_gs = oracle.sspmm_bwd(ip, ix, va, grad.numpy(), sel, deg=deg.numpy())
+    exp_xgrad = oracle.scatter_dense(exp_gs, cols)
+    res = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank)) for rank in range(world)]
+    assert int(res[0]["lo"]) == 0 and int(res[0]["hi"]) == int(res[1]["lo"]) and int(res[1]["hi"]) == g["v_num"]
+    assert int(res[0]["m"]) == int(res[1]["m"]) == max(int(r["hi"]) - int(r["lo"]) for r in res)
+    assert int(res[0]["edges"]) + int(res[1]["edges"]) == g["e_num"]
+    assert abs(int(res[0]["edges"]) - int(res[1]["edges"])) <= int(np.diff(ip).max())
+    uniform_split = abs(2 * int(ip[slab_rows(g["v_num"], world)]) - g["e_num"])
+    assert abs(int(res[0]["edges"]) - int(res[1]["edges"])) <= uniform_split       # never worse than equal rows
+    for rank, r in enumerate(res):
+        lo, hi = int(r["lo"]), int(r["hi"])
+        assert_close(r["out"][: hi - lo], exp_out[lo:hi], "rank %d forward" % rank)
+        assert_close(r["gs"][: hi - lo], exp_gs[lo:hi], "rank %d backward" % rank)
+        assert_close(r["xgrad"][: hi - lo], exp_xgrad[lo:hi], "rank %d autograd" % rank)
+        assert not r["out"][hi - lo:].any() and not r["gs"][hi - lo:].any()       # padding rows stay zero
+
+
+def test_balanced_bounds_and_padded_positions():
+    from sharded import balanced_bounds, padded_position, uniform_bounds
+    ip = torch.tensor([0, 0, 0, 50, 50, 51, 52, 100, 100])           # 8 rows, 100 edges, two hubs
+    assert balanced_bounds(ip, 1) == [0, 8]
+    b = balanced_bounds(ip, 2)
+    assert b[0] == 0 and b[-1] == 8 and b == sorted(b)
+    assert abs(int(ip[b[1]]) - 50) <= 50
+    b4 = balanced_bounds(ip, 4)
+    assert len(b4) == 5 and b4 == sorted(b4) and b4[-1] == 8
+    # identity for the equal-row partition, owner * m + offset otherwise (empty slabs own nothing)
+    ids = torch.arange(10)
+    assert torch.equal(padded_position(ids, uniform_bounds(10, 3), 4), ids)
+    pos = padded_position(torch.arange(9), [0, 5, 5, 5, 9], 5)
+    assert pos.tolist() == [0, 1, 2, 3, 4, 15, 16, 17, 18]
+    # a hub-heavy graph: every rank gets its share of edges, all of them exactly once
+    g = synth_graph(300, 9000, seed=5, kind="powerlaw")
+    for world in (2, 4, 8):
+        bounds = balanced_bounds(g["indptr"], world)
+        per_rank = [shard_rows(g, world, r, bounds)["e_num"] for r in range(world)]
+        assert sum(per_rank) == 9000
+        assert max(per_rank) <= 9000 // world + int((g["indptr"][1:] - g["indptr"][:-1]).max())
+        m = shard_rows(g, world, 0, bounds)["v_num"]
+        assert all(shard_rows(g, world, r, bounds)["v_num"] == m for r in range(world))
+        assert sum(shard_columns(g, world, r, bounds)["e_num"] for r in range(world)) == 9000
 
 
 def test_partition_helpers_cover_the_graph_exactly():
