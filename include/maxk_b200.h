@@ -67,6 +67,9 @@ const char *maxk_status_string(int status);
  *   idx_i64    [n_rows, k]   int64  (nullable; the dtype torch.topk returns)
  *   masked     [n_rows, dim] fp32   (nullable; x with every non-selected entry set to 0 =
  *                                    the MaxK nonlinearity output, maxk_models_integrated.py:28-37)
+ * For dim == 256, x and masked must be 16-byte aligned (MAXK_ERR_ALIGN otherwise); when they are 32-byte
+ * aligned (any torch allocation) and order == MAXK_ORDER_BANKED with k in {8, 16, 32, 64}, the
+ * specialised kernel of the fused layer runs (32-byte loads), else the general one.  Same results.
  */
 int maxk_banked_modulus(int k); /* 4, 4, 8, 16 for k = 8, 16, 32, 64; 1 otherwise */
 int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
