@@ -55,6 +55,31 @@ def test_topk_ties_lowest_column(kern):
             assert np.array_equal(np.isnan(got), np.isnan(ev)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(ev))
 
 
+@pytest.mark.parametrize("k", [8, 16, 32, 64])
+def test_topk_general_and_specialised_kernels_agree(kern, k):
+    """dim 256 / banked order / k in {8,16,32,64} runs the specialised kernel when the rows are 32-byte aligned
+    and the general one otherwise (include/maxk_b200.h): a feature matrix that starts 16 bytes into a buffer
+    must give bit-identical CBSR, indices and masked rows."""
+    gen = torch.Generator().manual_seed(100 + k)
+    x = torch.randn(1031, 256, generator=gen)
+    x[5] = 1.0                                       # ties straddling rank k
+    x[6, ::3] = float("nan")
+    x[7] = torch.tensor([0.0, -0.0] * 128)
+    buf = torch.empty(1031 * 256 + 4, device="cuda")
+    shifted = buf[4:].view(1031, 256)
+    shifted.copy_(x)
+    aligned = x.cuda()
+    assert aligned.data_ptr() % 32 == 0 and shifted.data_ptr() % 32 == 16
+    a = kern.topk_cbsr(aligned, k, order=2, want_i32=True, want_masked=True)
+    b = kern.topk_cbsr(shifted, k, order=2, want_i32=True, want_masked=True)
+    ev, ec = oracle.topk(x.numpy(), k, 2)
+    for r in (a, b):
+        assert np.array_equal(r["sel"].cpu().numpy(), ec.astype(np.uint8))
+        assert np.array_equal(r["i32"].cpu().numpy(), ec)
+    assert torch.equal(a["values"].view(torch.int32), b["values"].view(torch.int32))
+    assert torch.equal(a["masked"].view(torch.int32), b["masked"].view(torch.int32))
+
+
 @pytest.mark.parametrize("dim,k", [(64, 8), (100, 19), (255, 32), (7, 7), (1, 1)])
 def test_topk_other_dims(kern, dim, k):
     x = torch.randn(333, dim, generator=torch.Generator().manual_seed(dim))
