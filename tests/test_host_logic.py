@@ -120,3 +120,48 @@ def test_csr_to_csc_matches_scipy():
     assert np.array_equal(b_ptr.numpy(), ip)
     for r in (0, 7, 399):
         assert np.array_equal(b_idx.numpy()[ip[r]:ip[r + 1]], np.sort(ix[ip[r]:ip[r + 1]]))
+
+
+def test_sharding_of_any_graph_is_a_partition_of_its_edges():
+    """hypothesis: for random ragged graphs, world sizes and both partitions, the row slabs hold every edge
+    exactly once, padded column positions are a bijection onto the real rows of the padded numbering, and
+    re-assembling the slabs gives back A (as a dense matrix in the padded numbering)."""
+    from hypothesis import given, settings, strategies as st
+    from sharded import balanced_bounds, padded_position, shard_columns, shard_rows, uniform_bounds
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 60), st.integers(1, 8), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def check(n, world, seed, balanced):
+        rng = np.random.default_rng(seed)
+        deg = rng.integers(0, 12, n)
+        deg[rng.random(n) < 0.3] = 0
+        if rng.random() < 0.5:
+            deg[rng.integers(0, n)] += 200                   # a hub
+        indptr = np.zeros(n + 1, np.int64)
+        indptr[1:] = np.cumsum(deg)
+        e = int(indptr[-1])
+        g = {"indptr": torch.from_numpy(indptr.astype(np.int32)), "indices": torch.from_numpy(rng.integers(0, n, e).astype(np.int32)),
+             "values": torch.from_numpy(rng.standard_normal(e).astype(np.float32)), "v_num": n, "e_num": e}
+        bounds = balanced_bounds(g["indptr"], world) if balanced else uniform_bounds(n, world)
+        assert bounds[0] == 0 and bounds[-1] == n and len(bounds) == world + 1 and bounds == sorted(bounds)
+        explicit = bounds if balanced else None
+        slabs = [shard_rows(g, world, r, explicit) for r in range(world)]
+        m = slabs[0]["v_num"]
+        assert all(s["v_num"] == m for s in slabs) and sum(s["e_num"] for s in slabs) == e
+        pos = padded_position(torch.arange(n), bounds, m)
+        assert len(set(pos.tolist())) == n and int(pos.max()) < world * m
+        dense = np.zeros((n, n))
+        rows = np.repeat(np.arange(n), deg)
+        np.add.at(dense, (rows, g["indices"].numpy()), g["values"].numpy().astype(np.float64))
+        padded = np.zeros((world * m, world * m))
+        padded[np.ix_(pos.numpy(), pos.numpy())] = dense
+        rebuilt, rebuilt_cols = np.zeros_like(padded), np.zeros_like(padded)
+        for r, s in enumerate(slabs):
+            lrows = np.repeat(np.arange(m), np.diff(s["indptr"].numpy()))
+            np.add.at(rebuilt, (r * m + lrows, s["indices"].numpy()), s["values"].numpy().astype(np.float64))
+            c = shard_columns(g, world, r, explicit)
+            crows = np.repeat(np.arange(world * m), np.diff(c["indptr"].numpy()))
+            np.add.at(rebuilt_cols, (crows, r * m + c["indices"].numpy()), c["values"].numpy().astype(np.float64))
+        assert np.array_equal(rebuilt, padded) and np.array_equal(rebuilt_cols, padded)
+
+    check()
