@@ -254,6 +254,29 @@ def mask_apply(dense, sel, add_vals=None):
     return out
 
 
+def maxk_layer_forward(indptr, indices, values, x, k, row_div=None, want_masked=False):
+    """The layer's forward in one call (additive): top-k -> CBSR -> SpGEMM with the fused divisor.
+    Returns (out [N, 256], cbsr_val [N, k], cbsr_sel [N, k] uint8, masked [N, D] or None); keep cbsr_sel for
+    maxk_layer_backward.  What MaxK.forward + MaxKSpGEMMFunction.forward do in the reference
+    (maxk_models_integrated.py:28-37 + maxk_spgemm_function.py:51-86: two torch.topk, a scatter, the kernel,
+    a division) as two kernel launches."""
+    indptr = _cuda(indptr, "indptr", torch.int32)
+    r = topk_cbsr(x, k, order=ORDER_BANKED, want_masked=want_masked)
+    out = spgemm_forward_csr(indptr[:-1], indptr[1:], indices, values, r["values"], r["sel"], row_div=row_div)
+    return out, r["values"], r["sel"], r["masked"]
+
+
+def maxk_layer_backward(indptr, indices, values, grad_output, cbsr_sel, row_div=None, dense_dim=None):
+    """The layer's backward in one call: gs [N, k] = sample_sel(A^T (grad_output / row_div)); with dense_dim the
+    gradient is also scattered to [N, dense_dim] (what maxk_spgemm_function.py:152-175 returns for
+    input_features).  Returns gs, or (gs, dense)."""
+    indptr = _cuda(indptr, "indptr", torch.int32)
+    gs = sspmm_backward_csr(indptr[:-1], indptr[1:], indices, values, grad_output, cbsr_sel, row_div=row_div)
+    if dense_dim is None:
+        return gs
+    return gs, cbsr_scatter(gs, cbsr_sel, dim=int(dense_dim))
+
+
 def build_warp4(indptr, warp_max_nz=WARP_MAX_NZ):
     """GPU replacement of kernels/generate_meta.py: returns (warp4 int32[4W], W)."""
     indptr = _cuda(indptr, "indptr", torch.int32)

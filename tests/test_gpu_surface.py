@@ -215,6 +215,25 @@ def test_optimized_operator_matches_v4_on_an_undirected_graph():
         OptimizedMaxKSpmmWrapper("g").spmm(cix, cva, x[:, :k], None, cip, deg, deg, t_idx, t_val)
 
 
+def test_fused_layer_entry_points():
+    """maxk_layer_forward / maxk_layer_backward (additive) against the oracle, with the fused divisor."""
+    import maxk_cuda_kernels as kern
+    k = 32
+    p = make_problem(900, 40000, k, kind="powerlaw", seed=12, signed=True)
+    ip, ix, va = graph_np(p["graph"])
+    cip, cix, cva = graph_cuda(p["graph"])
+    deg = np.maximum(np.diff(ip), 1).astype(np.float32)
+    out, vals, sel, masked = kern.maxk_layer_forward(cip, cix, cva, p["x"].cuda(), k, row_div=_t(deg), want_masked=True)
+    assert np.array_equal(sel.cpu().numpy(), p["cbsr_sel"]) and np.array_equal(vals.cpu().numpy(), p["cbsr_val"])
+    assert np.array_equal(masked.cpu().numpy(), oracle.maxk_act_fwd(p["x"].numpy(), p["cbsr_col"]))
+    assert_close(out, oracle.spgemm_fwd(ip, ix, va, p["cbsr_val"], p["cbsr_sel"], deg=deg), "layer forward")
+    gs, dense = kern.maxk_layer_backward(cip, cix, cva, p["grad"].cuda(), sel, row_div=_t(deg), dense_dim=256)
+    want = oracle.sspmm_bwd(ip, ix, va, p["grad"].numpy(), p["cbsr_sel"], deg=deg)
+    assert_close(gs, want, "layer backward")
+    assert_close(dense, oracle.scatter_dense(want, p["cbsr_col"]), "layer backward, dense")
+    assert kern.maxk_layer_backward(cip, cix, cva, p["grad"].cuda(), sel).shape == (900, k)
+
+
 def test_gradcheck_like_adjoint_identity():
     """<fwd(x_vals), g> == <x_vals, bwd(g)> on the GPU kernels themselves."""
     import maxk_cuda_kernels as kern
