@@ -5,17 +5,20 @@
 // (kernels/maxk_kernel.cu:23-96), which quantises to 8 bits, emits the FIRST k elements above a
 // pivot rather than the top k and is hard-wired to k = 32.
 //
-// One warp per row, the row lives in registers (8 values per lane for dim = 256, loaded as two
-// coalesced float4).  Exact selection:
+// One warp per row, the row lives in registers (8 values per lane).  Exact selection:
 //   1. keys  = order-preserving uint32 image of the floats (NaN largest, -0 == +0);
-//   2. bisection in KEY space between the row's min and max key: count(key >= mid) with one
-//      warp REDUX per step; stops as soon as a threshold with exactly k keys above it is found
-//      (about log2(256)+2 steps on continuous data, at most 33 when ties straddle rank k);
+//   2. a threshold search in KEY space: the bracket starts at the minimum over lanes of each lane's
+//      ceil(k/32)-th largest key (at least k keys lie at or above it), pivots come from a secant step on
+//      the counts (a plain bisection every fourth step), count(key >= pivot) is one warp REDUX per step;
+//      it stops as soon as exactly k keys lie at or above the pivot (5.3 counts per row on U[0,1) data,
+//      6.5 on N(0,1); at most ~128 when ties straddle rank k);
 //   3. every key > T is selected; of the keys == T the lowest columns are taken until k;
 //   4. the output position of every selected entry is computed from 8 warp ballots with
-//      popcounts only (no shuffles): column order (MAXK_ORDER_COLUMN_ASC), bank-residue-major
-//      order (MAXK_ORDER_BANKED, what the SpGEMM/SSpMM kernels are conflict-minimal on), or
-//      rank-sorted by (value desc, column asc) through shared memory (MAXK_ORDER_VALUE_DESC).
+//      popcounts: column order (MAXK_ORDER_COLUMN_ASC), bank-residue-major order (MAXK_ORDER_BANKED,
+//      what the SpGEMM/SSpMM kernels are conflict-minimal on), or rank-sorted by (value desc, column
+//      asc) through shared memory (MAXK_ORDER_VALUE_DESC).
+// Two kernels: topk_banked_kernel<K> for the layer's hot configuration (dim 256, banked order,
+// k in {8, 16, 32, 64}; see its header below) and the general topk_cbsr_kernel for everything else.
 // The same pass can write the dense masked row (the MaxK nonlinearity output), so the
 // reference's topk + zeros_like + scatter_ + multiply (4 dense passes) is one read + one write.
 #include "maxk_common.cuh"
