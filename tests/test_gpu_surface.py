@@ -215,6 +215,50 @@ def test_optimized_operator_matches_v4_on_an_undirected_graph():
         OptimizedMaxKSpmmWrapper("g").spmm(cix, cva, x[:, :k], None, cip, deg, deg, t_idx, t_val)
 
 
+def test_operators_match_reference_operator_glue():
+    """ref_ops.npz = the reference's v3 / v4 / optimized autograd operators run on the CPU
+    (tests/golden/make_golden_ops.py); ours on the GPU, same inputs, same call signatures."""
+    import spgemmfunction as opt_mod
+    import spgemmfunction_v3 as v3_mod
+    import spgemmfunction_v4 as v4_mod
+    from graph_loader import csr_to_csc
+    import maxk_cuda_kernels as kern
+    r = np.load(os.path.join(GOLD, "ref_ops.npz"))
+    k = 32
+    # v3 (13 arguments), with the reference's grad_output masking switched on
+    ip, ix, va = _t(r["v3_indptr"]), _t(r["v3_indices"]), _t(r["v3_values"])
+    t_ptr, t_idx, t_val = csr_to_csc(ip, ix, va)
+    in_deg = (ip[1:] - ip[:-1]).clamp(min=1).float()
+    out_deg = (t_ptr[1:] - t_ptr[:-1]).clamp(min=1).float()
+    w_csr, n_csr = kern.build_warp4(ip)
+    w_csc, n_csc = kern.build_warp4(t_ptr)
+    x = _t(r["v3_x"]).requires_grad_(True)
+    v3_mod.MaxKSpGEMMFunction.reference_compat = True
+    try:
+        y = v3_mod.maxk_spgemm(ix, va, x, k, w_csr, n_csr, ip, in_deg, out_deg, t_idx, t_val, w_csc, n_csc)
+        y.backward(_t(r["v3_up"]))
+    finally:
+        v3_mod.MaxKSpGEMMFunction.reference_compat = False
+    assert_close(y, r["v3_out"], "v3 forward vs the reference operator")
+    assert_close(x.grad, r["v3_grad_input"], "v3 grad_input vs the reference operator")
+    # v4 (8 arguments) and optimized (11 arguments): torch.topk output passed in as the reference's callers do
+    ip, ix, va = _t(r["u_indptr"]), _t(r["u_indices"]), _t(r["u_values"])
+    deg = (ip[1:] - ip[:-1]).clamp(min=1).float()
+    w, nw = kern.build_warp4(ip)
+    t_ptr, t_idx, t_val = csr_to_csc(ip, ix, va)
+    ti = _t(r["u_topk_indices"])
+    tv = _t(r["u_topk_values"]).requires_grad_(True)
+    y4 = v4_mod.maxk_spgemm(ix, va, tv, ti, w, nw, ip, deg)
+    y4.backward(_t(r["u_up"]))
+    assert_close(y4, r["v4_out"], "v4 forward vs the reference operator")
+    assert_close(tv.grad, r["v4_grad_topk_values"], "v4 grad_topk_values vs the reference operator")
+    tv = _t(r["u_topk_values"]).requires_grad_(True)
+    yo = opt_mod.optimized_maxk_spgemm(ix, va, tv, ti, w, nw, ip, deg, deg, t_idx, t_val)
+    yo.backward(_t(r["u_up"]))
+    assert_close(yo, r["opt_out"], "optimized forward vs the reference operator")
+    assert_close(tv.grad, r["opt_grad_topk_values"], "optimized grad_topk_values vs the reference operator")
+
+
 def test_fused_layer_entry_points():
     """maxk_layer_forward / maxk_layer_backward (additive) against the oracle, with the fused divisor."""
     import maxk_cuda_kernels as kern

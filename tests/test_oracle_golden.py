@@ -119,3 +119,36 @@ def test_forward_backward_are_adjoint():
     lhs = float((oracle.spgemm_fwd(indptr, indices, values, vals, sel).astype(np.float64) * g).sum())
     rhs = float((vals.astype(np.float64) * oracle.sspmm_bwd(indptr, indices, values, g, sel)).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_oracle_matches_reference_operator_glue():
+    """ref_ops.npz: the reference's v3 / v4 / optimized autograd operators executed on the CPU
+    (tests/golden/make_golden_ops.py).  Pins WHERE the degree divisions happen, which arrays the backward
+    walks, and the v3 quirk of masking grad_output with the input's top-k pattern (spgemmfunction_v3.py:118)."""
+    r = np.load(os.path.join(GOLD, "ref_ops.npz"))
+    k = 32
+    # v3: CSR forward / in_degrees, backward over the CSC arrays / out_degrees, grad_output masked first
+    ip, ix, va, x, up = r["v3_indptr"], r["v3_indices"], r["v3_values"], r["v3_x"], r["v3_up"]
+    n = len(ip) - 1
+    import scipy.sparse as sp
+    csc = sp.csr_matrix((va, ix, ip), shape=(n, n)).tocsc()
+    csc.sort_indices()
+    t_ptr, t_idx, t_val = csc.indptr.astype(np.int32), csc.indices.astype(np.int32), csc.data.astype(np.float32)
+    in_deg = np.maximum(np.diff(ip), 1).astype(np.float32)
+    out_deg = np.maximum(np.diff(t_ptr), 1).astype(np.float32)
+    vals, cols = oracle.topk(x, k, 0)
+    sel = cols.astype(np.uint8)
+    np.testing.assert_allclose(oracle.spgemm_fwd(ip, ix, va, vals, sel, deg=in_deg), r["v3_out"], rtol=1e-5, atol=1e-6)
+    mask = np.zeros_like(x)
+    np.put_along_axis(mask, cols.astype(np.int64), 1.0, axis=1)
+    gs = oracle.sspmm_bwd(t_ptr, t_idx, t_val, up * mask, sel, deg=out_deg)
+    np.testing.assert_allclose(oracle.scatter_dense(gs, cols), r["v3_grad_input"], rtol=1e-5, atol=1e-6)
+    # v4 / optimized: pre-computed torch.topk, undirected graph, one degree vector on both sides
+    ip, ix, va, up = r["u_indptr"], r["u_indices"], r["u_values"], r["u_up"]
+    tv, ti = r["u_topk_values"], r["u_topk_indices"]
+    deg = np.maximum(np.diff(ip), 1).astype(np.float32)
+    out = oracle.spgemm_fwd(ip, ix, va, tv, ti.astype(np.uint8), deg=deg)
+    gs = oracle.sspmm_bwd(ip, ix, va, up, ti.astype(np.uint8), deg=deg)
+    for name in ("v4", "opt"):
+        np.testing.assert_allclose(out, r[name + "_out"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(gs, r[name + "_grad_topk_values"], rtol=1e-5, atol=1e-6)
