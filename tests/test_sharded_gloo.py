@@ -188,33 +188,32 @@ def _sage_reference(params, a, deg, x, k):
     return h @ params["lin_out.weight"].t() + params["lin_out.bias"]
 
 
-def _sage_worker(rank, world, port, result_dir):
+def _sage_worker(rank, world, port, result_dir, partition="rows"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g, x, grad, deg, k = _problem(n=150, e=2500, k=16)
-        n, m = g["v_num"], slab_rows(g["v_num"], world)
         torch.manual_seed(7)                                   # identical weights on every rank
-        model = ShardedMaxKSAGE(g, 256, 256, 2, 5, maxk=k, compute=OracleCompute())
-        lo = rank * m
-        rows = max(0, min(n, lo + m) - lo)
-        x_local = torch.zeros(m, 256)
-        x_local[:rows] = x[lo:lo + rows]
+        model = ShardedMaxKSAGE(g, 256, 256, 2, 5, maxk=k, compute=OracleCompute(), partition=partition)
+        rows = model.agg.valid_rows()
+        x_local = model.agg.local_slab(x)
         out = model(x_local)
         out[:rows].square().sum().backward()                   # loss over the real rows of this rank
         allreduce_gradients(model)
         np.savez(os.path.join(result_dir, "sage%d.npz" % rank), out=out.detach().numpy(),
+                 lo=model.agg.rows["row_lo"], hi=model.agg.rows["row_hi"],
                  **{"g_" + name: p.grad.numpy() for name, p in model.named_parameters()},
                  **{"p_" + name: p.detach().numpy() for name, p in model.named_parameters()})
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_sage_matches_single_process_model(tmp_path):
+@pytest.mark.parametrize("partition", ["rows", "nnz"])
+def test_sharded_sage_matches_single_process_model(tmp_path, partition):
     world = 2
-    mp.spawn(_sage_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_sage_worker, args=(world, _free_port(), str(tmp_path), partition), nprocs=world, join=True)
     g, x, grad, deg, k = _problem(n=150, e=2500, k=16)
-    n, m = g["v_num"], slab_rows(g["v_num"], world)
+    n = g["v_num"]
     r0 = np.load(os.path.join(str(tmp_path), "sage0.npz"))
     params = {key[2:]: torch.from_numpy(r0[key]).requires_grad_(True) for key in r0.files if key.startswith("p_")}
     a = torch.sparse_csr_tensor(g["indptr"].long(), g["indices"].long(), g["values"], size=(n, n))
@@ -222,7 +221,7 @@ def test_sharded_sage_matches_single_process_model(tmp_path):
     ref.square().sum().backward()
     for rank in range(world):
         r = np.load(os.path.join(str(tmp_path), "sage%d.npz" % rank))
-        lo, hi = rank * m, min(n, rank * m + m)
+        lo, hi = int(r["lo"]), int(r["hi"])
         np.testing.assert_allclose(r["out"][: hi - lo], ref.detach().numpy()[lo:hi], rtol=2e-4, atol=2e-4)
         for name, p in params.items():                      # summed over ranks == gradient of the full loss
             np.testing.assert_allclose(r["g_" + name], p.grad.numpy(), rtol=2e-3, atol=2e-3, err_msg=name)
