@@ -110,3 +110,61 @@ def test_second_point_from_the_lane_maxima_keeps_the_bracket_valid():
             assert set(np.nonzero(key >= t0)[0]) == set(np.nonzero(key >= t1)[0])
             saved += s0 - s1
     assert saved > 0
+
+
+def _popc(x):
+    return bin(x).count("1")
+
+
+def _banked_positions(sel_cols, k):
+    """Mirror of the position computation of topk_banked_kernel<K>: lane l owns columns 8l .. 8l+7, bs[s] is
+    the ballot of slot s; returns the column stored at every output position."""
+    m = 16 if k == 64 else 8 if k == 32 else 4
+    selb = np.zeros((32, 8), bool)
+    for c in sel_cols:
+        selb[c // 8, c % 8] = True
+    bs = [sum(1 << lane for lane in range(32) if selb[lane, s]) for s in range(8)]
+    out = {}
+    for lane in range(32):
+        lt = (1 << lane) - 1
+        pos = [0] * 8
+        if m == 8:                       # class == slot
+            base = 0
+            for s in range(8):
+                pos[s] = base + _popc(bs[s] & lt)
+                base += _popc(bs[s])
+        elif m == 4:                     # class == slot & 3; inside a class: (lane, slot < 4 first)
+            base = 0
+            for u in range(4):
+                pos[u] = base + _popc(bs[u] & lt) + _popc(bs[u + 4] & lt)
+                pos[u + 4] = pos[u] + (1 if selb[lane, u] else 0)
+                base += _popc(bs[u]) + _popc(bs[u + 4])
+        else:                            # class == 8 * (lane & 1) + slot
+            pm = 0xaaaaaaaa if lane & 1 else 0x55555555
+            mine = [_popc(bs[s] & pm) for s in range(8)]
+            base = (k - sum(mine)) if lane & 1 else 0
+            for s in range(8):
+                pos[s] = base + _popc(bs[s] & pm & lt)
+                base += mine[s]
+        for s in range(8):
+            if selb[lane, s]:
+                assert pos[s] not in out
+                out[pos[s]] = 8 * lane + s
+    return [out[i] for i in range(k)]
+
+
+@pytest.mark.parametrize("k", [8, 16, 32, 64])
+def test_banked_position_formulas_give_the_banked_order(k):
+    """MAXK_ORDER_BANKED = entries sorted by (column mod m, column), m = maxk_banked_modulus(k): the ballot /
+    popcount formulas of the specialised kernel produce exactly that permutation for any selected set."""
+    m = 16 if k == 64 else 8 if k == 32 else 4
+    rng = np.random.default_rng(k)
+    for t in range(400):
+        pool = 256 if t % 4 else max(k, 64)          # every fourth case: columns clustered in the first lanes
+        cols = rng.choice(pool, k, replace=False).tolist()
+        assert _banked_positions(cols, k) == sorted(cols, key=lambda c: (c % m, c))
+    import oracle
+    x = rng.standard_normal((50, 256)).astype(np.float32)
+    _, oc = oracle.topk(x, k, 2)                      # ... and it is the order the oracle emits
+    for r in range(50):
+        assert _banked_positions(oc[r].tolist(), k) == oc[r].tolist()
