@@ -54,3 +54,27 @@ def test_product_code_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "libmaxk_oracle" not in text and "libmaxk_ref" not in text, f
+
+
+def test_header_is_plain_c_and_a_c_host_links_against_the_library(tmp_path):
+    """The boundary is a C ABI, not a C++ one: the header compiles as C99 on its own, and the plain-C host in
+    examples/ (the binding a cgo / JNI / Rust caller would write) compiles and links against libmaxk_b200.so
+    with nothing but the CUDA runtime.  (It is not run here: no GPU.)"""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    assert gcc, "no C compiler"
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include "maxk_b200.h"\nint main(void) { int (*f)(void) = maxk_abi_version; return f == 0; }\n')
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                    str(probe)], check=True)
+    cuda = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        import pytest
+        pytest.skip("CUDA toolkit headers not found")
+    exe = tmp_path / "c_host_layer"
+    subprocess.run([gcc, "-std=c99", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(ROOT, "examples", "c_host_layer.c"), "-L", os.path.dirname(LIB), "-lmaxk_b200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-Wl,-rpath," + os.path.dirname(LIB),
+                    "-o", str(exe)], check=True, env={k: v for k, v in os.environ.items() if k not in ("CC", "CXX")})
+    assert exe.exists()
