@@ -49,9 +49,14 @@ const char *maxk_status_string(int status);
 /* top-k output order */
 #define MAXK_ORDER_VALUE_DESC 0 /* (value desc, column asc): torch.topk(sorted=True) order */
 #define MAXK_ORDER_COLUMN_ASC 1 /* column ascending                                        */
-#define MAXK_ORDER_BANKED 2     /* (column mod m, column) ascending, m = maxk_banked_modulus(k): the order
-                                   on which (2)/(3) have the fewest shared-memory bank conflicts; the
-                                   fused layer uses it.  Equal to COLUMN_ASC when m == 1.      */
+#define MAXK_ORDER_BANKED 2     /* the order on which (2) has the fewest shared-memory bank conflicts; the fused
+                                   layer uses it.  m = maxk_banked_modulus(k).  m == 1: column ascending.
+                                   m == 4 (k in {8,16,32,64,96,128}): residue classes column mod 4, the class
+                                   with the most entries first (ties: lower class), columns ascending inside
+                                   a class; the entry of sorted rank p is stored at position p for k < 32 and
+                                   at 32*(i/8) + 8*t + i%8, t = p/(k/4), i = p%(k/4), for k >= 32 (lane t of a
+                                   4-lane slot owns k/4 consecutive ranks as 8-entry runs).  Every consumer
+                                   accepts any entry order; only speed depends on it.             */
 
 /*
  * (1) MaxK row-wise top-k -> CBSR.
@@ -68,10 +73,10 @@ const char *maxk_status_string(int status);
  *   masked     [n_rows, dim] fp32   (nullable; x with every non-selected entry set to 0 =
  *                                    the MaxK nonlinearity output, maxk_models_integrated.py:28-37)
  * For dim == 256, x and masked must be 16-byte aligned (MAXK_ERR_ALIGN otherwise); when they are 32-byte
- * aligned (any torch allocation) and order == MAXK_ORDER_BANKED with k in {8, 16, 32, 64}, the
+ * aligned (any torch allocation) and order == MAXK_ORDER_BANKED with k in {8, 16, 32, 64, 96, 128}, the
  * specialised kernel of the fused layer runs (32-byte loads), else the general one.  Same results.
  */
-int maxk_banked_modulus(int k); /* 4, 4, 8, 16 for k = 8, 16, 32, 64; 1 otherwise */
+int maxk_banked_modulus(int k); /* 4 for k in {8, 16, 32, 64, 96, 128}; 1 otherwise */
 int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
                    float *cbsr_val, uint8_t *cbsr_sel, int32_t *idx_i32, int64_t *idx_i64,
                    float *masked, maxk_stream_t stream);
@@ -84,8 +89,18 @@ int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
  *   out      [n_rows, dim] fp32, fully written (rows without edges become 0)
  *   row_div  [n_rows] fp32 nullable: out[r,:] /= row_div[r] fused into the epilogue
  *            (the reference does it in Python: maxk_spgemm_function.py:86, spgemmfunction_v4:72)
- *   workspace: maxk_spgemm_workspace_bytes(n_rows) bytes of device scratch.
- * Deterministic: each output row is reduced in a fixed order (no atomics).
+ *   workspace: maxk_spgemm_workspace_bytes(n_rows) bytes of device scratch, 16-byte aligned.
+ * out must be 32-byte aligned when dim == 256.  Deterministic: each output row is reduced in a fixed order
+ * (no atomics).  k in {8, 16, 32, 64, 96, 128} with 32-byte aligned cbsr_val / 8-byte aligned cbsr_sel run the
+ * vectorised kernels, every other k in [1, 256] a scalar-load variant of the same scheme.
+ *
+ * The kernel walks the rows in the order of a ROW PLAN (rows sorted by degree bucket and cut into work items,
+ * the GPU-built counterpart of the reference's warp4 partitioning, kernels/generate_meta.py:30-48).
+ * maxk_spgemm_forward builds the plan into the workspace on every call (three small kernels, no host
+ * read-back); a caller that runs many layers / epochs on one graph builds it once with maxk_plan_build and
+ * calls maxk_spgemm_forward_planned:
+ *   plan       maxk_plan_bytes(n_rows) bytes, 16-byte aligned; a pure function of (row_begin, row_end, device)
+ *   workspace  maxk_plan_workspace_bytes(n_rows) bytes of scratch, free again when the build has run
  */
 int maxk_spgemm_forward(const int32_t *row_begin, const int32_t *row_end,
                         const int32_t *indices, const float *values,
@@ -93,6 +108,15 @@ int maxk_spgemm_forward(const int32_t *row_begin, const int32_t *row_end,
                         float *out, int64_t n_rows, int64_t n_edges, int dim, int k,
                         const float *row_div,
                         void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+size_t maxk_plan_bytes(int64_t n_rows);
+size_t maxk_plan_workspace_bytes(int64_t n_rows);
+int maxk_plan_build(const int32_t *row_begin, const int32_t *row_end, int64_t n_rows,
+                    void *plan, size_t plan_bytes, void *workspace, size_t workspace_bytes,
+                    maxk_stream_t stream);
+int maxk_spgemm_forward_planned(const void *plan, const int32_t *indices, const float *values,
+                                const float *cbsr_val, const uint8_t *cbsr_sel,
+                                float *out, int64_t n_rows, int64_t n_edges, int dim, int k,
+                                const float *row_div, maxk_stream_t stream);
 
 /*
  * (3) Backward outer-product SSpMM: gs = sample_sel(A^T (g / row_div)).

@@ -62,27 +62,47 @@ static int kc_cmp(const void *a, const void *b)
  *   out_sel  [N, k] int32  their columns
  * order = 0: entries sorted (value desc, column asc)   -- torch.topk(sorted=True) order
  * order = 1: entries sorted by column ascending
- * order = 2: entries sorted by (column mod bank_mod, column) -- the order our fused kernels emit
- *            (a pure permutation of the same k entries; consumers are order independent)
+ * order = 2: MAXK_ORDER_BANKED, the order our fused kernels emit (a pure permutation of the same k entries;
+ *            consumers are order independent).  With bank_mod = m > 1: residue classes column mod m, the
+ *            class with the most entries first (ties: lower class), columns ascending inside a class; the
+ *            entry of sorted rank p is stored at position p for k < 32 and, for k >= 32, at
+ *            32 * (i / 8) + 8 * t + i % 8 with t = p / (k/4), i = p % (k/4) (lane t of a 4-lane slot owns k/4
+ *            consecutive ranks, kept as 8-entry runs per 32-entry chunk).  bank_mod <= 1: column order.
  */
 void oracle_topk(const float *x, int64_t N, int D, int k, float *out_val, int32_t *out_sel, int order, int bank_mod)
 {
 #pragma omp parallel
     {
         kc_t *buf = (kc_t *)malloc(sizeof(kc_t) * (size_t)D);
+        kc_t *tmp = (kc_t *)malloc(sizeof(kc_t) * (size_t)D);
 #pragma omp for schedule(static)
         for (int64_t r = 0; r < N; ++r) {
             const float *row = x + r * D;
             for (int j = 0; j < D; ++j) { buf[j].key = order_key(row[j]); buf[j].col = j; }
             qsort(buf, (size_t)D, sizeof(kc_t), kc_cmp);
             if (order == 1 || order == 2) {
-                /* re-sort the chosen k by (col mod m, col): simple insertion sort */
                 const int m = (order == 2 && bank_mod > 1) ? bank_mod : 1;
+                int size[64] = {0}, rank[64];
+                for (int i = 0; i < k; ++i) size[buf[i].col % m]++;
+                for (int u = 0; u < m; ++u) {              /* classes by (size desc, class asc) */
+                    rank[u] = 0;
+                    for (int v = 0; v < m; ++v)
+                        if (v != u && (size[v] > size[u] || (size[v] == size[u] && v < u))) rank[u]++;
+                }
+                /* sort the chosen k by (class rank, col): simple insertion sort */
                 for (int i = 1; i < k; ++i) {
                     kc_t t = buf[i]; int j = i - 1;
-                    while (j >= 0 && (buf[j].col % m > t.col % m ||
+                    while (j >= 0 && (rank[buf[j].col % m] > rank[t.col % m] ||
                                       (buf[j].col % m == t.col % m && buf[j].col > t.col))) { buf[j + 1] = buf[j]; --j; }
                     buf[j + 1] = t;
+                }
+                if (m > 1 && k >= 32) {                    /* rank -> position in the row */
+                    const int epl = k / 4;
+                    for (int p = 0; p < k; ++p) {
+                        const int t = p / epl, i = p % epl;
+                        tmp[32 * (i / 8) + 8 * t + i % 8] = buf[p];
+                    }
+                    for (int p = 0; p < k; ++p) buf[p] = tmp[p];
                 }
             }
             for (int i = 0; i < k; ++i) {
@@ -91,6 +111,7 @@ void oracle_topk(const float *x, int64_t N, int D, int k, float *out_val, int32_
             }
         }
         free(buf);
+        free(tmp);
     }
 }
 

@@ -64,12 +64,12 @@ def num_threads():
 
 
 def banked_modulus(k):
-    return {8: 4, 16: 4, 32: 8, 64: 16}.get(k, 1)
+    return 4 if k in (8, 16, 32, 64, 96, 128) else 1
 
 
 def topk(x, k, order=0):
     """(values fp32 [N,k], columns int32 [N,k]); order 0 = (value desc, col asc), 1 = column asc,
-    2 = (col mod banked_modulus(k), col) asc."""
+    2 = MAXK_ORDER_BANKED (classes col mod 4 by size, see maxk_oracle.c)."""
     x = _f32(x)
     n, d = x.shape
     vals = np.empty((n, k), np.float32)

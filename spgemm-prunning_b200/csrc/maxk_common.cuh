@@ -48,10 +48,11 @@ struct Lay {
     __device__ static __forceinline__ int word(int col) { return (col / L) * 32 + (col % L); }  // + q * L
 };
 
-// bank-residue modulus used by MAXK_ORDER_BANKED for a given k (host + device)
+// residue modulus of MAXK_ORDER_BANKED for a given k (host + device): 4 = the lanes per slot of slots.cuh
+// for the k that have a vectorised path, 1 (plain column order) otherwise
 __host__ __device__ inline int banked_modulus(int k)
 {
-    return k == 8 ? 4 : k == 16 ? 4 : k == 32 ? 8 : k == 64 ? 16 : 1;
+    return (k == 8 || k == 16 || k == 32 || k == 64 || k == 96 || k == 128) ? 4 : 1;
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

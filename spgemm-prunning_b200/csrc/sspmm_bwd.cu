@@ -275,7 +275,16 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
     }
 }
 
-int pick_rows_per_grab(int64_t n_rows, int64_t n_edges, int total_warps);  // spgemm_fwd.cu
+static int pick_rows_per_grab(int64_t n_rows, int64_t n_edges, int total_warps)
+{
+    const int64_t avg = n_rows > 0 ? (n_edges + n_rows - 1) / n_rows : 1;
+    int64_t by_balance = n_rows / (8 * (int64_t)total_warps);  // keep >= 8 grabs per warp
+    int64_t by_work = 2048 / (avg > 0 ? avg : 1);              // <= ~2048 edges per grab
+    int64_t g = by_balance < by_work ? by_balance : by_work;
+    if (g < 1) g = 1;
+    if (g > 32) g = 32;
+    return (int)g;
+}
 
 template <int K>
 static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const int *idx, const float *val,

@@ -40,6 +40,17 @@ __device__ __forceinline__ uint32_t fast_key(float v)
     return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 
+// MAXK_ORDER_BANKED: sorted rank p (classes mod 4 by size, columns ascending) -> position in the CBSR row.
+// Lane t of a slot (slots.cuh) takes the k/4 consecutive ranks [t k/4, (t+1) k/4) and processes the i-th of
+// them in its i-th instruction; for k >= 32 its entries are stored as 8-entry runs at 32 j + 8 t (one
+// 32-byte load per 32-entry chunk j), so rank p = t k/4 + 8 j + e lives at 32 j + 8 t + e.
+__host__ __device__ inline int banked_mem_pos(int p, int k)
+{
+    if (k < 32) return p;
+    const int epl = k >> 2, t = p / epl, i = p - t * epl;
+    return 32 * (i >> 3) + 8 * t + (i & 7);
+}
+
 // c_recip31[d] = floor(2^31 / d), d in [1, 256]; statically initialised so that no host-side copy is
 // needed (the first call may happen inside a CUDA-graph capture)
 __constant__ uint32_t c_recip31[kAccDim + 1] = {
@@ -124,10 +135,6 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
     const int warp = threadIdx.x >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * kTopkWarps;
     const unsigned lt = (1u << lane) - 1u;
-    // lanes whose columns fall in the same residue classes mod bank_mod as mine (bank_mod in {4,8,16})
-    const int groups = bank_mod >= 4 ? bank_mod / 4 : 1;
-    const int grp = lane % groups;
-    const unsigned cm = (groups == 1 ? 0xffffffffu : groups == 2 ? 0x55555555u : 0x11111111u) << grp;
 
     for (int64_t r = (int64_t)blockIdx.x * kTopkWarps + warp; r < n_rows; r += warps_total) {
         const float *row = x + r * dim;
@@ -235,24 +242,19 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
         for (int s = 0; s < 8; ++s) bs[s] = __ballot_sync(kFullT, selb[s]);
         int pos[8];
         if (ORDER == MAXK_ORDER_BANKED && bank_mod >= 4) {
-            // class of (lane, slot) = 4*grp + (slot&3); classes ascending, columns ascending inside
-            int c_lo[4], c_hi[4], mine = 0;
+            // class of (lane, slot) = slot & 3 (= column mod 4); classes by (size desc, class asc), columns
+            // ascending inside a class: all columns of the first half come before those of the second half
+            int sz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sz[u] = __popc(bs[u]) + __popc(bs[u + 4]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                c_lo[u] = __popc(bs[u] & cm);
-                c_hi[u] = __popc(bs[u + 4] & cm);
-                mine += c_lo[u] + c_hi[u];            // selected entries of my lane group
-            }
-            int base = 0;
-            for (int g = 0; g < groups - 1; ++g) {
-                const int tg = __shfl_sync(kFullT, mine, g);    // lane g belongs to group g
-                if (g < grp) base += tg;
-            }
+                int base = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                pos[u] = base + __popc(bs[u] & cm & lt);
-                pos[u + 4] = base + c_lo[u] + __popc(bs[u + 4] & cm & lt);
-                base += c_lo[u] + c_hi[u];
+                for (int v = 0; v < 4; ++v)
+                    if (v != u && (sz[v] > sz[u] || (sz[v] == sz[u] && v < u))) base += sz[v];
+                pos[u] = banked_mem_pos(base + __popc(bs[u] & lt), k);
+                pos[u + 4] = banked_mem_pos(base + __popc(bs[u]) + __popc(bs[u + 4] & lt), k);
             }
         } else {
             // column order: (half, lane, slot&3)
@@ -321,7 +323,6 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
                    uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32, int64_t *__restrict__ out_i64,
                    float *__restrict__ masked, int one)
 {
-    constexpr int M = K == 64 ? 16 : K == 32 ? 8 : 4;       // banked_modulus(K)
     __shared__ __align__(8) uint32_t s_ent[kTopkWarps][2 * K];   // (value bits, column id) pairs
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -350,7 +351,13 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
             m1 = max(m1, key[s]);
         }
         const uint32_t kmax = __reduce_max_sync(kFullT, m1);
-        const uint32_t kmin = __reduce_min_sync(kFullT, K > 32 ? m2 : m1);
+        uint32_t lane_lo = K > 32 ? m2 : m1;
+        if (K > 64) {                           // no per-lane rank bound beyond the 2nd largest: start at the row minimum
+            lane_lo = key[0];
+#pragma unroll
+            for (int s = 1; s < 8; ++s) lane_lo = min(lane_lo, key[s]);
+        }
+        const uint32_t kmin = __reduce_min_sync(kFullT, lane_lo);
         // small k: a second exact point for free.  Only lane maxima can exceed the largest second-largest
         // key M2 of any lane, so count(>= M2 + 1) is one ballot over the lane maxima; it cuts the long
         // tail above the threshold off the bracket (simulated: 4.7 -> 3.8 counts per row on U[0,1),
@@ -397,35 +404,21 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
         unsigned bs[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) bs[s] = __ballot_sync(kFullT, selb[s]);
+        // class == slot & 3; inside a class: (lane, slot < 4 first); classes by (size desc, class asc)
         int pos[8];
-        if (M == 8) {                    // class == slot
-            int base = 0;
+        {
+            int sz[4];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                pos[s] = base + __popc(bs[s] & lt);
-                base += __popc(bs[s]);
-            }
-        } else if (M == 4) {             // class == slot & 3; inside a class: (lane, slot < 4 first)
-            int base = 0;
+            for (int u = 0; u < 4; ++u) sz[u] = __popc(bs[u]) + __popc(bs[u + 4]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                pos[u] = base + __popc(bs[u] & lt) + __popc(bs[u + 4] & lt);
-                pos[u + 4] = pos[u] + (selb[u] ? 1 : 0);
-                base += __popc(bs[u]) + __popc(bs[u + 4]);
-            }
-        } else {                         // M == 16: class == 8 * (lane & 1) + slot
-            const unsigned pm = (lane & 1) ? 0xaaaaaaaau : 0x55555555u;   // lanes of my parity
-            int mine[8], total = 0;
+                int base = 0;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                mine[s] = __popc(bs[s] & pm);
-                total += mine[s];
-            }
-            int base = (lane & 1) ? K - total : 0;    // exactly K entries are selected: the even lanes hold K - odd
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                pos[s] = base + __popc(bs[s] & pm & lt);
-                base += mine[s];
+                for (int v = 0; v < 4; ++v)
+                    if (v != u && (sz[v] > sz[u] || (sz[v] == sz[u] && v < u))) base += sz[v];
+                const int p = base + __popc(bs[u] & lt) + __popc(bs[u + 4] & lt);
+                pos[u] = banked_mem_pos(p, K);
+                pos[u + 4] = banked_mem_pos(p + (selb[u] ? 1 : 0), K);
             }
         }
 
@@ -607,7 +600,9 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
             case 8: err = launch_topk_banked<8>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
             case 16: err = launch_topk_banked<16>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
             case 32: err = launch_topk_banked<32>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-            default: err = launch_topk_banked<64>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+            case 64: err = launch_topk_banked<64>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+            case 96: err = launch_topk_banked<96>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
+            default: err = launch_topk_banked<128>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
         }
         return status_from_cuda(err);
     }

@@ -27,7 +27,7 @@ WARP_MAX_NZ = 64        # kernels/generate_meta.py:9
 
 ORDER_VALUE_DESC = 0
 ORDER_COLUMN_ASC = 1
-ORDER_BANKED = 2          # (column mod banked_modulus(k), column): fewest bank conflicts in fwd/bwd
+ORDER_BANKED = 2          # residue classes mod 4 by size (include/maxk_b200.h): fewest bank conflicts in the forward
 
 _c_i64 = ctypes.c_int64
 _c_int = ctypes.c_int
@@ -47,6 +47,11 @@ _SIGNATURES = {
     "maxk_sspmm_backward_accumulate": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
                                                 _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_spgemm_workspace_bytes": (_c_size, [_c_i64]),
+    "maxk_plan_bytes": (_c_size, [_c_i64]),
+    "maxk_plan_workspace_bytes": (_c_size, [_c_i64]),
+    "maxk_plan_build": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr, _c_size, _c_ptr, _c_size, _c_ptr]),
+    "maxk_spgemm_forward_planned": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_int, _c_int,
+                                             _c_ptr, _c_ptr]),
     "maxk_warp4_workspace_bytes": (_c_size, [_c_i64]),
     "maxk_warp4_scan": (_c_int, [_c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_warp4_fill": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr]),
@@ -105,9 +110,91 @@ def _cuda(t, name, dtype=None):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# One scratch buffer per (device, stream): calls on a stream are ordered, so they can share it (the
+# reference allocates nothing per call either; round 1 did a torch.empty per op).
+_ws_cache = {}
+
+
 def _workspace(n_rows, device):
     nbytes = _lib.maxk_spgemm_workspace_bytes(n_rows)
-    return torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device=device), nbytes
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((nbytes + 255) // 256 * 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf, nbytes
+
+
+class RowPlan:
+    """The forward kernel's row plan (csrc/plan.cu) of one CSR row structure: build once per graph, pass as
+    `plan=` to spgemm_forward_csr.  Holds the device buffer and the row count it was built for."""
+
+    def __init__(self, buf, n_rows, device):
+        self.buf, self.n_rows, self.device = buf, n_rows, device
+
+    def header(self):
+        """(n_rows, shared long rows, separate groups, shared last-wave rows, trailing separate groups, items) --
+        one device->host read, for reports and tests."""
+        h = self.buf[:64].view(torch.int32).tolist()
+        return {"n_rows": h[1], "long_rows": h[2], "groups": h[3], "last_wave_rows": h[4], "tail_groups": h[5], "items": h[8]}
+
+
+def build_plan(row_begin, row_end):
+    """GPU-built row plan for (row_begin, row_end) (for a plain CSR: indptr[:-1], indptr[1:])."""
+    row_begin = _cuda(row_begin, "row_begin", torch.int32)
+    row_end = _cuda(row_end, "row_end", torch.int32)
+    n_rows = row_begin.numel()
+    _check(row_end.numel() == n_rows, "row_begin / row_end length mismatch")
+    dev = row_begin.device
+    pb, wb = _lib.maxk_plan_bytes(n_rows), _lib.maxk_plan_workspace_bytes(n_rows)
+    buf = torch.empty((pb + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+    ws = torch.empty((wb + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _status(_lib.maxk_plan_build(_ptr(row_begin), _ptr(row_end), n_rows, _ptr(buf), pb, _ptr(ws), wb, _stream(row_begin)),
+                "maxk_plan_build")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    return RowPlan(buf, n_rows, dev)
+
+
+# indptr tensor -> RowPlan, rebuilt only when the tensor object or its version changes (the operators receive
+# graph_indptr on every call; a graph object keeps it alive, so the weak reference identifies it safely)
+_indptr_plans = {}
+
+
+def plan_for_indptr(indptr):
+    """(row_begin, row_end, RowPlan) of a CSR indptr tensor, cached per tensor object."""
+    if indptr.dtype != torch.int32:
+        indptr = indptr.to(torch.int32)            # a temporary: planned for this call only
+    key = id(indptr)
+    hit = _indptr_plans.get(key)
+    if hit is not None:
+        ref, version, plan, ready = hit
+        if ref() is indptr and version == indptr._version:
+            torch.cuda.current_stream(indptr.device).wait_event(ready)
+            return indptr[:-1], indptr[1:], plan
+    _check(indptr.is_cuda and indptr.dim() == 1 and indptr.numel() >= 1, "graph_indptr must be a 1-D CUDA tensor")
+    indptr = indptr if indptr.is_contiguous() else indptr.contiguous()
+    plan = build_plan(indptr[:-1], indptr[1:])
+    if len(_indptr_plans) > 64:
+        for k in [k for k, v in _indptr_plans.items() if v[0]() is None]:
+            del _indptr_plans[k]
+    try:
+        _indptr_plans[key] = (weakref.ref(indptr), indptr._version, plan, _ready_event(indptr.device))
+    except TypeError:
+        pass
+    return indptr[:-1], indptr[1:], plan
+
+
+def rows_and_plan(warp4_metadata, num_warps, graph_indptr, n_rows):
+    """Row edge ranges + row plan from the CSR indptr when given, else from the warp4 quads."""
+    if graph_indptr is not None:
+        return plan_for_indptr(graph_indptr)
+    if warp4_metadata is None:
+        raise RuntimeError("maxk_spgemm needs warp4_metadata or graph_indptr (there is no fallback path)")
+    rows = _rows_from_warp4(warp4_metadata, int(num_warps), n_rows)
+    torch.cuda.current_stream(warp4_metadata.device).wait_event(rows[3])
+    return rows[0], rows[1], rows[2]
 
 
 # warp4 tensor -> (row_begin, row_end), rebuilt only when the tensor object or its version changes
@@ -126,6 +213,7 @@ def _rows_from_warp4(warp4, num_warps, n_rows):
     with torch.cuda.device(warp4.device):
         _status(_lib.maxk_warp4_to_rows(_ptr(warp4), num_warps, n_rows, _ptr(rows[0]), _ptr(rows[1]),
                                         _stream(warp4)), "maxk_warp4_to_rows")
+    rows = (rows[0], rows[1], build_plan(rows[0], rows[1]) if n_rows > 0 else None, _ready_event(warp4.device))
     if len(_rows_cache) > 64:
         for k in [k for k, v in _rows_cache.items() if v[0]() is None]:
             del _rows_cache[k]
@@ -139,9 +227,26 @@ def _rows_from_warp4(warp4, num_warps, n_rows):
 # ----------------------------------------------------------------------------------------------
 # CSR-native entry points (additive API; the warp4 entry points below reduce to these)
 # ----------------------------------------------------------------------------------------------
+def _ready_event(device):
+    """Event recorded on the current stream: cached per-graph data built here is waited for by other streams."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    return ev
+
+
+def _check_graph(indices, n_src, row_end, where):
+    """Opt-in (MAXK_VALIDATE=1) bounds check of the graph arrays: malformed input otherwise becomes out-of-bounds
+    device gathers / reductions instead of an exception."""
+    if os.environ.get("MAXK_VALIDATE", "0") != "1" or indices.numel() == 0:
+        return
+    _check(int(indices.min()) >= 0 and int(indices.max()) < n_src, "%s: a column index is outside [0, %d)" % (where, n_src))
+    _check(int(row_end.max()) <= indices.numel(), "%s: a row range ends past the edge arrays" % where)
+
+
 def spgemm_forward_csr(row_begin, row_end, indices, values, cbsr_val, cbsr_sel, out_dim=FULL_DIM,
-                       row_div=None, out=None):
-    """out[n_rows, out_dim] = A_csr x scatter(CBSR), optionally / row_div (fused)."""
+                       row_div=None, out=None, plan=None):
+    """out[n_rows, out_dim] = A_csr x scatter(CBSR), optionally / row_div (fused).
+    plan: the RowPlan of (row_begin, row_end) (build_plan); without it the plan is rebuilt inside the call."""
     row_begin = _cuda(row_begin, "row_begin", torch.int32)
     row_end = _cuda(row_end, "row_end", torch.int32)
     indices = _cuda(indices, "indices", torch.int32)
@@ -160,12 +265,20 @@ def spgemm_forward_csr(row_begin, row_end, indices, values, cbsr_val, cbsr_sel, 
     else:
         _check(out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and
                tuple(out.shape) == (n_rows, out_dim), "out must be a contiguous fp32 CUDA [n_rows, out_dim] tensor")
+    _check_graph(indices, cbsr_val.size(0), row_end, "spgemm_forward")
     with torch.cuda.device(cbsr_val.device):
-        ws, ws_bytes = _workspace(n_rows, cbsr_val.device)
-        _status(_lib.maxk_spgemm_forward(_ptr(row_begin), _ptr(row_end), _ptr(indices), _ptr(values), _ptr(cbsr_val),
-                                         _ptr(cbsr_sel), _ptr(out), n_rows, indices.numel(), out_dim, k,
-                                         _ptr(row_div), _ptr(ws), ws_bytes, _stream(cbsr_val)),
-                "maxk_spgemm_forward")
+        if plan is not None:
+            _check(isinstance(plan, RowPlan) and plan.n_rows == n_rows and plan.device == cbsr_val.device,
+                   "plan was built for another row structure / device")
+            _status(_lib.maxk_spgemm_forward_planned(_ptr(plan.buf), _ptr(indices), _ptr(values), _ptr(cbsr_val),
+                                                     _ptr(cbsr_sel), _ptr(out), n_rows, indices.numel(), out_dim, k,
+                                                     _ptr(row_div), _stream(cbsr_val)), "maxk_spgemm_forward_planned")
+        else:
+            ws, ws_bytes = _workspace(n_rows, cbsr_val.device)
+            _status(_lib.maxk_spgemm_forward(_ptr(row_begin), _ptr(row_end), _ptr(indices), _ptr(values), _ptr(cbsr_val),
+                                             _ptr(cbsr_sel), _ptr(out), n_rows, indices.numel(), out_dim, k,
+                                             _ptr(row_div), _ptr(ws), ws_bytes, _stream(cbsr_val)),
+                    "maxk_spgemm_forward")
     return out
 
 
@@ -192,6 +305,7 @@ def sspmm_backward_csr(row_begin, row_end, indices, values, grad_output, cbsr_se
         _check(out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (n_dst, k),
                "out must be a contiguous fp32 CUDA [n_dst, k] tensor")
     fn = _lib.maxk_sspmm_backward_accumulate if accumulate else _lib.maxk_sspmm_backward
+    _check_graph(indices, n_dst, row_end, "sspmm_backward")
     with torch.cuda.device(grad_output.device):
         ws, ws_bytes = _workspace(n_rows, grad_output.device)
         _status(fn(_ptr(row_begin), _ptr(row_end), _ptr(indices), _ptr(values),
@@ -254,7 +368,7 @@ def mask_apply(dense, sel, add_vals=None):
     return out
 
 
-def maxk_layer_forward(indptr, indices, values, x, k, row_div=None, want_masked=False):
+def maxk_layer_forward(indptr, indices, values, x, k, row_div=None, want_masked=False, plan=None):
     """The layer's forward in one call (additive): top-k -> CBSR -> SpGEMM with the fused divisor.
     Returns (out [N, 256], cbsr_val [N, k], cbsr_sel [N, k] uint8, masked [N, D] or None); keep cbsr_sel for
     maxk_layer_backward.  What MaxK.forward + MaxKSpGEMMFunction.forward do in the reference
@@ -262,7 +376,9 @@ def maxk_layer_forward(indptr, indices, values, x, k, row_div=None, want_masked=
     a division) as two kernel launches."""
     indptr = _cuda(indptr, "indptr", torch.int32)
     r = topk_cbsr(x, k, order=ORDER_BANKED, want_masked=want_masked)
-    out = spgemm_forward_csr(indptr[:-1], indptr[1:], indices, values, r["values"], r["sel"], row_div=row_div)
+    if plan is None:
+        plan = plan_for_indptr(indptr)[2]
+    out = spgemm_forward_csr(indptr[:-1], indptr[1:], indices, values, r["values"], r["sel"], row_div=row_div, plan=plan)
     return out, r["values"], r["sel"], r["masked"]
 
 
@@ -307,7 +423,8 @@ def spmm_maxk_forward(warp4_metadata, indices, values, input_data, sparse_select
     _check(input_data.dim() == 2, "input_data must be [N, k]")
     _check(int(dim_sparse) == input_data.size(1), "dim_sparse must equal input_data.size(1)")
     rows = _rows_from_warp4(warp4_metadata, int(num_warps), input_data.size(0))
-    return spgemm_forward_csr(rows[0], rows[1], indices, values, input_data, sparse_selector, FULL_DIM)
+    torch.cuda.current_stream(input_data.device).wait_event(rows[3])     # the cache may have been filled on another stream
+    return spgemm_forward_csr(rows[0], rows[1], indices, values, input_data, sparse_selector, FULL_DIM, plan=rows[2])
 
 
 def spmm_maxk_backward(warp4_metadata, indices, values, grad_output, sparse_selector, num_warps, dim_sparse):
@@ -318,6 +435,7 @@ def spmm_maxk_backward(warp4_metadata, indices, values, grad_output, sparse_sele
     _check(grad_output.dim() == 2, "grad_output must be [N, D]")
     _check(int(dim_sparse) == sparse_selector.size(1), "dim_sparse must equal sparse_selector.size(1)")
     rows = _rows_from_warp4(warp4_metadata, int(num_warps), grad_output.size(0))
+    torch.cuda.current_stream(grad_output.device).wait_event(rows[3])
     return sspmm_backward_csr(rows[0], rows[1], indices, values, grad_output, sparse_selector)
 
 

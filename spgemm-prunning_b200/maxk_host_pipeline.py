@@ -33,6 +33,8 @@ class HostStagedMaxKLayer:
         self.sets = [{"x": mk(self.n, dim), "g": mk(self.n, dim), "out": mk(self.n, dim), "gs": mk(self.n, self.k),
                       "vals": mk(self.n, self.k), "sel": mk(self.n, self.k, dt=torch.uint8),
                       "done": None} for _ in range(2)]
+        # row plans of the slabs (the forward walks its rows in plan order, csrc/plan.cu)
+        self.plans = [K.build_plan(indptr[lo:hi], indptr[lo + 1:hi + 1]) for lo, hi in self.bounds]
         self.calls = 0
 
     def run(self, hx, hg, hout, hgs, block_current_stream=True):
@@ -62,7 +64,7 @@ class HostStagedMaxKLayer:
                             out_sel=b["sel"][lo:hi])
             for j, (lo, hi) in enumerate(self.bounds):
                 K.spgemm_forward_csr(self.ip[lo:hi], self.ip[lo + 1:hi + 1], self.ix, self.va, b["vals"], b["sel"],
-                                     out_dim=self.dim, out=b["out"][lo:hi])
+                                     out_dim=self.dim, out=b["out"][lo:hi], plan=self.plans[j])
                 ef[j].record(self.comp)
             b["gs"].zero_()
             for j, (lo, hi) in enumerate(self.bounds):
@@ -84,4 +86,4 @@ class HostStagedMaxKLayer:
             cur.wait_event(done)
         return done
 
-    launches_per_call = property(lambda self: len(self.bounds) * 5)   # top-k + (fwd, long) + (bwd, long) per slab
+    launches_per_call = property(lambda self: len(self.bounds) * 4)   # top-k + fwd + (bwd, long-row bwd) per slab

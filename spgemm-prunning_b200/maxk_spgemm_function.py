@@ -20,15 +20,8 @@ MAXK_KERNELS_AVAILABLE = True   # importing maxk_cuda_kernels raises if the libr
 
 
 def _row_ranges(warp4_metadata, num_warps, graph_indptr, n_rows):
-    """Row edge ranges from the CSR indptr when given, else from the warp4 quads."""
-    if graph_indptr is not None:
-        if graph_indptr.dtype != torch.int32:
-            graph_indptr = graph_indptr.to(torch.int32)
-        return graph_indptr[:-1], graph_indptr[1:]
-    if warp4_metadata is None:
-        raise RuntimeError("maxk_spgemm needs warp4_metadata or graph_indptr (there is no fallback path)")
-    rows = maxk_cuda_kernels._rows_from_warp4(warp4_metadata, int(num_warps), n_rows)
-    return rows[0], rows[1]
+    """(row_begin, row_end, row plan) from the CSR indptr when given, else from the warp4 quads."""
+    return maxk_cuda_kernels.rows_and_plan(warp4_metadata, num_warps, graph_indptr, n_rows)
 
 
 class MaxKSpGEMMFunction(Function):
@@ -46,7 +39,7 @@ class MaxKSpGEMMFunction(Function):
                 raise RuntimeError("feature dim %d > 256 cannot be addressed by uint8 selectors" % d)
             sparse_data = input_features.contiguous()
             sparse_selector = torch.arange(d, device=input_features.device, dtype=torch.uint8).repeat(n, 1)
-        row_begin, row_end = _row_ranges(warp4_metadata, num_warps, graph_indptr, n)
+        row_begin, row_end, plan = _row_ranges(warp4_metadata, num_warps, graph_indptr, n)
         bwd_indices = graph_indices_T if graph_indices_T is not None else graph_indices
         bwd_values = graph_values_T if graph_values_T is not None else graph_values
         saved_deg = out_degrees if out_degrees is not None else torch.empty(0, device=input_features.device)
@@ -55,7 +48,7 @@ class MaxKSpGEMMFunction(Function):
         ctx.input_shape = (n, d)
         return maxk_cuda_kernels.spgemm_forward_csr(
             row_begin, row_end, graph_indices, graph_values, sparse_data, sparse_selector,
-            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=in_degrees)          # :76-86
+            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=in_degrees, plan=plan)          # :76-86
 
     @staticmethod
     def backward(ctx, grad_output):

@@ -187,7 +187,10 @@ class CudaCompute:
 
     def spgemm(self, g, vals, sel, row_div=None):
         ip = g["indptr"]
-        return self.k.spgemm_forward_csr(ip[:-1], ip[1:], g["indices"], g["values"], vals, sel, row_div=row_div)
+        if g.get("plan") is None:                 # the slab's row plan, built once
+            g["plan"] = self.k.build_plan(ip[:-1], ip[1:])
+        return self.k.spgemm_forward_csr(ip[:-1], ip[1:], g["indices"], g["values"], vals, sel, row_div=row_div,
+                                         plan=g["plan"])
 
     def sspmm(self, g, grad, sel, row_div=None):
         ip = g["indptr"]

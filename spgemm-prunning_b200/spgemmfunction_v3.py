@@ -23,8 +23,7 @@ MAXK_KERNELS_AVAILABLE = True
 def _rows(warp4_metadata, num_warps, n_rows, what):
     if warp4_metadata is None:
         raise RuntimeError("%s metadata required" % what)                            # spgemmfunction_v3.py:57-58
-    rows = maxk_cuda_kernels._rows_from_warp4(warp4_metadata, int(num_warps), n_rows)
-    return rows[0], rows[1]
+    return maxk_cuda_kernels.rows_and_plan(warp4_metadata, num_warps, None, n_rows)
 
 
 class MaxKSpGEMMFunction(Function):
@@ -49,20 +48,19 @@ class MaxKSpGEMMFunction(Function):
             sparse_data = input_features.contiguous()
             sparse_selector = torch.arange(d, device=input_features.device, dtype=torch.uint8).repeat(n, 1)
         if graph_indptr is not None:
-            ip = graph_indptr if graph_indptr.dtype == torch.int32 else graph_indptr.to(torch.int32)
-            row_begin, row_end = ip[:-1], ip[1:]
             if warp4_metadata_csr is None:
                 raise RuntimeError("CSR metadata required")
+            row_begin, row_end, plan = maxk_cuda_kernels.plan_for_indptr(graph_indptr)
         else:
-            row_begin, row_end = _rows(warp4_metadata_csr, num_warps_csr, n, "CSR")
-        t_begin, t_end = _rows(warp4_metadata_csc, num_warps_csc, n, "CSC")
+            row_begin, row_end, plan = _rows(warp4_metadata_csr, num_warps_csr, n, "CSR")
+        t_begin, t_end, _ = _rows(warp4_metadata_csc, num_warps_csc, n, "CSC")
         saved_deg = out_degrees if out_degrees is not None else torch.empty(0, device=input_features.device)
         ctx.save_for_backward(graph_indices_T, graph_values_T, sparse_selector, t_begin, t_end, saved_deg)
         ctx.has_out_degrees = out_degrees is not None
         ctx.input_shape = (n, d)
         return maxk_cuda_kernels.spgemm_forward_csr(
             row_begin, row_end, graph_indices, graph_values, sparse_data, sparse_selector,
-            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=in_degrees)                   # :85-99
+            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=in_degrees, plan=plan)                   # :85-99
 
     @staticmethod
     def backward(ctx, grad_output):

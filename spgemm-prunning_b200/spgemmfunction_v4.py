@@ -23,11 +23,11 @@ class MaxKSpGEMMFunction(Function):
         if degrees is None:
             raise RuntimeError("degrees REQUIRED for normalization")              # :48
         sparse_selector = topk_indices if topk_indices.dtype == torch.uint8 else topk_indices.to(torch.uint8)  # :51
-        row_begin, row_end = _row_ranges(warp4_metadata, num_warps, graph_indptr, topk_values.size(0))
+        row_begin, row_end, plan = _row_ranges(warp4_metadata, num_warps, graph_indptr, topk_values.size(0))
         ctx.save_for_backward(graph_indices, graph_values, sparse_selector, degrees, row_begin, row_end)
         return maxk_cuda_kernels.spgemm_forward_csr(
             row_begin, row_end, graph_indices, graph_values, topk_values, sparse_selector,
-            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=degrees)                  # :61-72
+            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=degrees, plan=plan)                  # :61-72
 
     @staticmethod
     def backward(ctx, grad_output):

@@ -32,7 +32,7 @@ def test_python_binding_binds_exactly_the_header():
     assert sorted(k._SIGNATURES) == declared_functions()
     assert k._lib.maxk_abi_version() == 1
     assert k._lib.maxk_status_string(-2).decode().startswith("dim must")
-    assert [k._lib.maxk_banked_modulus(x) for x in (8, 16, 32, 64, 19)] == [4, 4, 8, 16, 1]
+    assert [k._lib.maxk_banked_modulus(x) for x in (8, 16, 32, 64, 96, 128, 19)] == [4, 4, 4, 4, 4, 4, 1]
     assert k._lib.maxk_spgemm_workspace_bytes(1000) >= 4000
 
 

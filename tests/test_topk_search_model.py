@@ -116,36 +116,44 @@ def _popc(x):
     return bin(x).count("1")
 
 
+def _mem_pos(p, k):
+    """banked_mem_pos of csrc/topk.cu: sorted rank -> position in the CBSR row."""
+    if k < 32:
+        return p
+    epl = k // 4
+    t, i = divmod(p, epl)
+    return 32 * (i // 8) + 8 * t + i % 8
+
+
+def _banked_reference(cols, k):
+    """MAXK_ORDER_BANKED by definition: classes column mod 4 by (size desc, class asc), columns ascending inside a
+    class, rank p stored at _mem_pos(p)."""
+    size = [sum(1 for c in cols if c % 4 == u) for u in range(4)]
+    rank = [sum(1 for v in range(4) if v != u and (size[v] > size[u] or (size[v] == size[u] and v < u))) for u in range(4)]
+    ordered = sorted(cols, key=lambda c: (rank[c % 4], c))
+    out = [None] * k
+    for p, c in enumerate(ordered):
+        out[_mem_pos(p, k)] = c
+    return out
+
+
 def _banked_positions(sel_cols, k):
     """Mirror of the position computation of topk_banked_kernel<K>: lane l owns columns 8l .. 8l+7, bs[s] is
     the ballot of slot s; returns the column stored at every output position."""
-    m = 16 if k == 64 else 8 if k == 32 else 4
     selb = np.zeros((32, 8), bool)
     for c in sel_cols:
         selb[c // 8, c % 8] = True
     bs = [sum(1 << lane for lane in range(32) if selb[lane, s]) for s in range(8)]
+    sz = [_popc(bs[u]) + _popc(bs[u + 4]) for u in range(4)]
     out = {}
     for lane in range(32):
         lt = (1 << lane) - 1
         pos = [0] * 8
-        if m == 8:                       # class == slot
-            base = 0
-            for s in range(8):
-                pos[s] = base + _popc(bs[s] & lt)
-                base += _popc(bs[s])
-        elif m == 4:                     # class == slot & 3; inside a class: (lane, slot < 4 first)
-            base = 0
-            for u in range(4):
-                pos[u] = base + _popc(bs[u] & lt) + _popc(bs[u + 4] & lt)
-                pos[u + 4] = pos[u] + (1 if selb[lane, u] else 0)
-                base += _popc(bs[u]) + _popc(bs[u + 4])
-        else:                            # class == 8 * (lane & 1) + slot
-            pm = 0xaaaaaaaa if lane & 1 else 0x55555555
-            mine = [_popc(bs[s] & pm) for s in range(8)]
-            base = (k - sum(mine)) if lane & 1 else 0
-            for s in range(8):
-                pos[s] = base + _popc(bs[s] & pm & lt)
-                base += mine[s]
+        for u in range(4):               # class == slot & 3; inside a class: (lane, slot < 4 first)
+            base = sum(sz[v] for v in range(4) if v != u and (sz[v] > sz[u] or (sz[v] == sz[u] and v < u)))
+            p = base + _popc(bs[u] & lt) + _popc(bs[u + 4] & lt)
+            pos[u] = _mem_pos(p, k)
+            pos[u + 4] = _mem_pos(p + (1 if selb[lane, u] else 0), k)
         for s in range(8):
             if selb[lane, s]:
                 assert pos[s] not in out
@@ -153,18 +161,17 @@ def _banked_positions(sel_cols, k):
     return [out[i] for i in range(k)]
 
 
-@pytest.mark.parametrize("k", [8, 16, 32, 64])
+@pytest.mark.parametrize("k", [8, 16, 32, 64, 96, 128])
 def test_banked_position_formulas_give_the_banked_order(k):
-    """MAXK_ORDER_BANKED = entries sorted by (column mod m, column), m = maxk_banked_modulus(k): the ballot /
-    popcount formulas of the specialised kernel produce exactly that permutation for any selected set."""
-    m = 16 if k == 64 else 8 if k == 32 else 4
+    """The ballot / popcount formulas of the specialised kernel produce exactly the MAXK_ORDER_BANKED permutation
+    for any selected set, and it is the order the oracle emits."""
     rng = np.random.default_rng(k)
     for t in range(400):
         pool = 256 if t % 4 else max(k, 64)          # every fourth case: columns clustered in the first lanes
         cols = rng.choice(pool, k, replace=False).tolist()
-        assert _banked_positions(cols, k) == sorted(cols, key=lambda c: (c % m, c))
+        assert _banked_positions(cols, k) == _banked_reference(cols, k)
     import oracle
     x = rng.standard_normal((50, 256)).astype(np.float32)
-    _, oc = oracle.topk(x, k, 2)                      # ... and it is the order the oracle emits
+    _, oc = oracle.topk(x, k, 2)
     for r in range(50):
         assert _banked_positions(oc[r].tolist(), k) == oc[r].tolist()
