@@ -28,7 +28,7 @@ for _p in (ROOT, os.path.join(ROOT, "spgemm-prunning_b200"), os.path.join(ROOT, 
 import torch  # noqa: E402
 
 DIM = 256
-KERNELS_PER_STEP = 5      # topk_cbsr, spgemm_fwd + its long-row kernel, sspmm_bwd + its long-row kernel
+KERNELS_PER_STEP = 4      # topk_banked, spgemm_fwd_slots, sspmm_bwd + its long-row kernel
 METRIC = "MaxK top-k + fwd SpGEMM + bwd SSpMM algorithmic HBM throughput, Reddit shape k=32"
 
 
@@ -54,10 +54,12 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(workload, kernel):
-    """dram read+write bytes per launch from the committed ncu --set full capture, or None."""
+    """Figures of the committed ncu --set full capture of `workload` (dram read+write bytes per launch, LSU
+    wavefronts per edge ...): one kernel's traffic, or the whole record when kernel is None."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(workload, {}).get(kernel)
+            rec = json.load(f).get(workload, {})
+            return rec if kernel is None else rec.get(kernel)
     except Exception:
         return None
 
@@ -170,8 +172,8 @@ def run_reference(args, n, e):
 
 
 def workload_config(args, n, e):
-    return {"workload": "synthetic %s-shape graph (%d nodes, %d edges, uniform kind, seed 123, U[0,1) edge values), "
-                        "hidden %d, k=%d: top-k + fwd SpGEMM + bwd SSpMM" % (args.shape, n, e, DIM, args.k),
+    return {"workload": "synthetic %s-shape graph (%d nodes, %d edges, %s kind, seed 123, U[0,1) edge values), "
+                        "hidden %d, k=%d: top-k + fwd SpGEMM + bwd SSpMM" % (args.shape, n, e, args.kind, DIM, args.k),
             "shape": args.shape, "nodes": n, "edges": e, "hidden": DIM, "k": args.k,
             "l2_note": "inputs per step (CSR 917 MB + features 239 MB + gradient 239 MB) exceed the 126 MB L2; no flush needed",
             "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs (%s partition), all_gather(CBSR) fwd, %s bwd" % (args.gpus, "equal-row" if args.partition == "rows" else "equal-edge", args.bwd_mode)}
@@ -180,6 +182,96 @@ def workload_config(args, n, e):
 # --------------------------------------------------------------------------------------------------
 # ours
 # --------------------------------------------------------------------------------------------------
+SWEEP = [("reddit", "uniform", 8), ("reddit", "uniform", 16), ("reddit", "uniform", 64), ("reddit", "powerlaw", 32),
+         ("flickr", "uniform", 32), ("yelp", "uniform", 32), ("proteins", "uniform", 64), ("products", "uniform", 32)]
+L2_GATHER_PEAK_TBS = 18.5      # tools/l2_bw.cu on B200: random 160-byte CBSR rows out of L2, 16-byte-per-lane loads
+L2_RED_PEAK_TBS = 6.2          # tools/l2_bw.cu: 128-byte red.global.add rows into an L2-resident target
+
+
+def _ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def _median_ms(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(_ev(), _ev()) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def parity_block(K, ip, ix, va, x, grad, vals, sel, out, gs, k, seed, rows_out=None, rows_gs=None, row_offset=0,
+                 n_samples=1024):
+    """Sampled-row check of one step's results against the C oracle (oracle/sampled_parity.py), outside the
+    timed region.  (ip, ix, va, x, grad, vals, sel) describe the WHOLE problem in global numbering; out / gs are
+    this process's result rows [row_offset, row_offset + rows)."""
+    import sampled_parity as sp
+    dev = ix.device
+    n_local = out.size(0) if rows_out is None else rows_out
+    idx = sp.sample_ids(n_local, n_samples, seed, dev)
+    sets_equal, vals_equal = sp.check_topk(x[idx + row_offset], vals[idx + row_offset], sel[idx + row_offset], k)
+    fv, fr = sp.check_forward(ip, ix, va, vals, sel, idx + row_offset, out[idx])
+    n_gs = gs.size(0) if rows_gs is None else rows_gs
+    idx2 = sp.sample_ids(n_gs, n_samples, seed + 1, dev)
+    bv, br, used = sp.check_backward(ip, ix, va, grad, sel, idx2 + row_offset, gs[idx2])
+    return {"topk_sets_equal": bool(sets_equal and vals_equal), "fwd_max_rel": fr, "bwd_max_rel": br,
+            "fwd_violation": fv, "bwd_violation": bv, "rows_checked": int(idx.numel()), "dst_rows_checked": used,
+            "tolerance": "index sets bit-exact; |got-exp| <= 1e-6 + 1e-5|exp| (violation <= 1)",
+            "ok": bool(sets_equal and vals_equal and fv <= 1.0 and bv <= 1.0)}
+
+
+def sweep_group(K, shape, kind, ks, dev, peak, ref):
+    """Secondary configurations on one graph (BASELINE.json configs 1, 3, 4, 5 and the k sweep of config 2): our
+    three kernels, the reference's kernels recompiled for sm_100a on the same inputs (checker leg, oracle/_ref),
+    and a sampled parity check."""
+    from synth_graphs import SHAPES, synth_graph
+    n, e = SHAPES[shape]
+    g = synth_graph(n, e, seed=123, kind=kind, device=dev)
+    ip, ix, va = g["indptr"], g["indices"], g["values"]
+    rb, re_ = ip[:-1], ip[1:]
+    gen = torch.Generator(device=dev).manual_seed(123)
+    x = torch.rand(n, DIM, device=dev, generator=gen)
+    grad = torch.rand(n, DIM, device=dev, generator=gen)
+    plan = K.build_plan(rb, re_)
+    out = torch.empty(n, DIM, device=dev)
+    max_deg = int((re_ - rb).max())
+    w4 = None
+    res = []
+    for k in ks:
+        gs = torch.empty(n, k, device=dev)
+        r = K.topk_cbsr(x, k, order=K.ORDER_BANKED)
+        t_topk = _median_ms(lambda: K.topk_cbsr(x, k, order=K.ORDER_BANKED, out_values=r["values"], out_sel=r["sel"]))
+        t_fwd = _median_ms(lambda: K.spgemm_forward_csr(rb, re_, ix, va, r["values"], r["sel"], out=out, plan=plan))
+        t_bwd = _median_ms(lambda: K.sspmm_backward_csr(rb, re_, ix, va, grad, r["sel"], out=gs))
+        b_topk, b_fwd, b_bwd = layer_bytes(n, e, k)
+        frac = lambda byt, ms: byt / (ms * 1e-3) / 1e9 / peak
+        ent = {"shape": shape, "kind": kind, "k": k, "nodes": n, "edges": e, "max_degree": max_deg,
+               "topk_ms": t_topk, "fwd_ms": t_fwd, "bwd_ms": t_bwd, "layer_ms": t_topk + t_fwd + t_bwd,
+               "topk_frac": frac(b_topk, t_topk), "fwd_frac": frac(b_fwd, t_fwd), "bwd_frac": frac(b_bwd, t_bwd),
+               "layer_frac": frac(b_topk + b_fwd + b_bwd, t_topk + t_fwd + t_bwd)}
+        try:
+            ent["parity"] = parity_block(K, ip, ix, va, x, grad, r["values"], r["sel"], out, gs, k, seed=7, n_samples=256)
+        except Exception as ex:   # the checker must not take the measurement down
+            ent["parity"] = {"ok": False, "error": repr(ex)[:200]}
+        if ref is not None:
+            try:
+                if w4 is None:
+                    w4 = K.build_warp4(ip)
+                ent["ref_fwd_ms"] = _median_ms(lambda: ref.ref_cuda_forward(w4[0], ix, va, r["values"], r["sel"], w4[1]), 1, 3)
+                ent["ref_bwd_ms"] = _median_ms(lambda: ref.ref_cuda_backward(w4[0], ix, va, grad, r["sel"], w4[1]), 1, 3)
+            except Exception as ex:
+                ent["ref_error"] = repr(ex)[:200]
+        res.append(ent)
+        del gs, r
+    return res
+
+
 def run_ours(args, n, e):
     import torch.distributed as dist
     import maxk_cuda_kernels as K          # raises if libmaxk_b200.so is missing: no fallback
@@ -193,12 +285,11 @@ def run_ours(args, n, e):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     k = args.k
-    graph = synth_graph(n, e, seed=123, kind="uniform", device=dev)
+    graph = synth_graph(n, e, seed=123, kind=args.kind, device=dev)
     gen = torch.Generator(device=dev).manual_seed(123)
     b_topk, b_fwd, b_bwd = layer_bytes(n, e, k)
     total_bytes = b_topk + b_fwd + b_bwd
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)
     nvml_index = local
     try:
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -207,28 +298,32 @@ def run_ours(args, n, e):
     except (ValueError, IndexError):
         nvml_index = local
     sampler = ClockSampler(nvml_index)
+    parity = None
+    sweep = None
 
     if world == 1:
         ip = graph["indptr"]
         rb, re_, ix, va = ip[:-1], ip[1:], graph["indices"], graph["values"]
+        plan = K.build_plan(rb, re_)                       # once per graph, like the reference's warp4 metadata
         x = torch.rand(n, DIM, device=dev, generator=gen)
         grad = torch.rand(n, DIM, device=dev, generator=gen)
         out = torch.empty(n, DIM, device=dev)
         gs = torch.empty(n, k, device=dev)
+        cb = {"values": torch.empty(n, k, device=dev), "sel": torch.empty(n, k, dtype=torch.uint8, device=dev)}
 
         def step(marks=None):
-            r = K.topk_cbsr(x, k, order=K.ORDER_BANKED)
+            K.topk_cbsr(x, k, order=K.ORDER_BANKED, out_values=cb["values"], out_sel=cb["sel"])
             if marks:
                 marks[0].record()
-            K.spgemm_forward_csr(rb, re_, ix, va, r["values"], r["sel"], out=out)
+            K.spgemm_forward_csr(rb, re_, ix, va, cb["values"], cb["sel"], out=out, plan=plan)
             if marks:
                 marks[1].record()
-            K.sspmm_backward_csr(rb, re_, ix, va, grad, r["sel"], out=gs)
+            K.sspmm_backward_csr(rb, re_, ix, va, grad, cb["sel"], out=gs)
 
         for _ in range(max(args.warmup, 3)):
             step()
         torch.cuda.synchronize()
-        marks = [(ev(), ev(), ev(), ev()) for _ in range(args.steps)]
+        marks = [(_ev(), _ev(), _ev(), _ev()) for _ in range(args.steps)]
         sampler.start()
         torch.cuda.synchronize()
         for s in range(args.steps):
@@ -242,6 +337,9 @@ def run_ours(args, n, e):
         t_fwd = sum(m[1].elapsed_time(m[2]) for m in marks) / args.steps
         t_bwd = sum(m[2].elapsed_time(m[3]) for m in marks) / args.steps
 
+        if not args.no_parity:
+            parity = parity_block(K, ip, ix, va, x, grad, cb["values"], cb["sel"], out, gs, k, seed=11)
+
         # ---- e2e: host buffers in, host buffers out, through the host-buffer operator API --------
         # (maxk_host_pipeline.HostStagedMaxKLayer: same kernels, copies overlapped with compute slab by slab;
         #  every step copies its inputs host->device and its results device->host inside the timed region)
@@ -250,13 +348,14 @@ def run_ours(args, n, e):
         hg = torch.empty(n, DIM, pin_memory=True).copy_(grad)
         hout = torch.empty(n, DIM, pin_memory=True)
         hgs = torch.empty(n, k, pin_memory=True)
+        ref_out_rows = out[:4096].cpu()
         del x, grad, out, gs
         staged = HostStagedMaxKLayer(ip, ix, va, k, dim=DIM, slabs=8)
         for _ in range(3):
             staged.run(hx, hg, hout, hgs)
         torch.cuda.synchronize()
         e2e_steps = max(3, min(args.steps, 10))
-        a, b = ev(), ev()
+        a, b = _ev(), _ev()
         a.record()
         for _ in range(e2e_steps):
             done = staged.run(hx, hg, hout, hgs, block_current_stream=False)
@@ -264,6 +363,9 @@ def run_ours(args, n, e):
         b.record()
         torch.cuda.synchronize()
         t_e2e = a.elapsed_time(b) / e2e_steps
+        if parity is not None:       # the host-buffer path must deliver the same rows as the device-resident one
+            parity["e2e_matches_device_path"] = bool(torch.allclose(hout[:4096], ref_out_rows, rtol=1e-5, atol=1e-6))
+            parity["ok"] = bool(parity["ok"] and parity["e2e_matches_device_path"])
         e2e_launches = staged.launches_per_call * e2e_steps
         h2d, d2h = 2 * n * DIM * 4, n * DIM * 4 + n * k * 4
         launches = KERNELS_PER_STEP * args.steps
@@ -271,14 +373,36 @@ def run_ours(args, n, e):
                  "e2e_note": "8 row slabs, h2d / compute / d2h on three streams, consecutive steps double-buffered"}
         roof_bytes, roof_ms = b_fwd, t_fwd
         scaling = "strong"
+        del staged, hx, hg, hout, hgs, graph, ip, ix, va, rb, re_, plan
+        torch.cuda.empty_cache()
+        if not args.no_sweep and args.shape == "reddit" and args.k == 32 and args.scale == 1.0:
+            peak0, _ = measured_peak_gbs()
+            ref = None
+            try:
+                import oracle
+                if oracle.ref_cuda_available():
+                    ref = oracle
+            except Exception:
+                ref = None
+            sweep = []
+            groups = []
+            for shape, kind, kk in SWEEP:
+                if groups and groups[-1][0] == (shape, kind):
+                    groups[-1][1].append(kk)
+                else:
+                    groups.append(((shape, kind), [kk]))
+            for (shape, kind), kks in groups:
+                try:
+                    sweep.extend(sweep_group(K, shape, kind, kks, dev, peak0, ref))
+                except Exception as ex:
+                    sweep.append({"shape": shape, "kind": kind, "k": kks, "error": repr(ex)[:200]})
+                torch.cuda.empty_cache()
     else:
-        from sharded import ShardedMaxKAggregation
+        from sharded import ShardedMaxKAggregation, _all_gather, padded_position
         layer = ShardedMaxKAggregation(graph, k, backward_mode=args.bwd_mode, partition=args.partition)
         m = layer.m
-        x = torch.rand(m, DIM, device=dev, generator=gen)
-        grad = torch.rand(m, DIM, device=dev, generator=gen)
-        del graph
-        torch.cuda.empty_cache()
+        x = torch.rand(m, DIM, device=dev, generator=torch.Generator(device=dev).manual_seed(123 + rank))
+        grad = torch.rand(m, DIM, device=dev, generator=torch.Generator(device=dev).manual_seed(1123 + rank))
 
         def step():
             out_l = layer.forward(x)
@@ -291,10 +415,10 @@ def run_ours(args, n, e):
         dist.barrier()
         torch.cuda.synchronize()
         sampler.start()
-        a, b = ev(), ev()
+        a, b = _ev(), _ev()
         a.record()
         for _ in range(args.steps):
-            step()
+            out_l, gs_l = step()
         b.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -303,29 +427,53 @@ def run_ours(args, n, e):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_step = float(t.item())
 
+        if not args.no_parity:
+            # every rank checks sampled rows of ITS output slabs against the oracle on the whole problem
+            # (features, gradients and CBSR all-gathered outside the timed region; the full graph is still resident)
+            pos = padded_position(torch.arange(n, device=dev), layer.bounds, m)
+            x_g = _all_gather(x, None)[pos]
+            g_g = _all_gather(grad, None)[pos]
+            vals_l, sel_l = layer.compute.topk(x, k)
+            vals_g = _all_gather(vals_l, None)[pos]
+            sel_g = _all_gather(sel_l, None)[pos]
+            valid = layer.valid_rows()
+            p = parity_block(K, graph["indptr"], graph["indices"], graph["values"], x_g, g_g, vals_g, sel_g, out_l, gs_l, k,
+                             seed=11 + rank, rows_out=valid, rows_gs=valid, row_offset=layer.rows["row_lo"]) if valid > 0 else \
+                {"topk_sets_equal": True, "fwd_violation": 0.0, "bwd_violation": 0.0, "fwd_max_rel": 0.0, "bwd_max_rel": 0.0,
+                 "rows_checked": 0, "dst_rows_checked": 0, "ok": True}
+            red = torch.tensor([p["fwd_violation"], p["bwd_violation"], p["fwd_max_rel"], p["bwd_max_rel"],
+                                0.0 if p["topk_sets_equal"] else 1.0, 0.0 if p["ok"] else 1.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            cnt = torch.tensor([p["rows_checked"], p["dst_rows_checked"]], device=dev, dtype=torch.int64)
+            dist.all_reduce(cnt)
+            red = red.tolist()
+            parity = {"topk_sets_equal": red[4] == 0.0, "fwd_max_rel": red[2], "bwd_max_rel": red[3], "fwd_violation": red[0],
+                      "bwd_violation": red[1], "rows_checked": int(cnt[0]), "dst_rows_checked": int(cnt[1]), "ranks": world,
+                      "tolerance": "index sets bit-exact; |got-exp| <= 1e-6 + 1e-5|exp| (violation <= 1), max over ranks",
+                      "ok": red[5] == 0.0}
+            del x_g, g_g, vals_g, sel_g, pos
+        del graph, out_l, gs_l
+        torch.cuda.empty_cache()
+
+        # ---- e2e: every rank streams its slab through its own PCIe link (three-stream chunk pipeline) ----
+        from maxk_host_pipeline import ShardedHostStagedLayer
         hx = torch.empty(m, DIM, pin_memory=True).copy_(x)
         hg = torch.empty(m, DIM, pin_memory=True).copy_(grad)
         hout = torch.empty(m, DIM, pin_memory=True)
         hgs = torch.empty(m, k, pin_memory=True)
-        dx, dg = torch.empty_like(x), torch.empty_like(grad)
-
-        def e2e_step():
-            dx.copy_(hx, non_blocking=True)
-            dg.copy_(hg, non_blocking=True)
-            out_l = layer.forward(dx)
-            gs_l = layer.backward(dg)
-            hout.copy_(out_l, non_blocking=True)
-            hgs.copy_(gs_l, non_blocking=True)
-
-        for _ in range(2):
-            e2e_step()
+        del x, grad
+        staged = ShardedHostStagedLayer(layer, dim=DIM, slabs=4)
+        for _ in range(3):
+            staged.run(hx, hg, hout, hgs)
         torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         e2e_steps = max(3, min(args.steps, 10))
-        a, b = ev(), ev()
+        a, b = _ev(), _ev()
         a.record()
         for _ in range(e2e_steps):
-            e2e_step()
+            done = staged.run(hx, hg, hout, hgs, block_current_stream=False)
+        torch.cuda.current_stream().wait_event(done)
         b.record()
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b) / e2e_steps], device=dev)
@@ -333,7 +481,8 @@ def run_ours(args, n, e):
         t_e2e = float(t.item())
         h2d, d2h = world * 2 * m * DIM * 4, world * (m * DIM * 4 + m * k * 4)
         launches = KERNELS_PER_STEP * args.steps * world
-        parts = {"wire_bytes_per_rank": layer.wire_bytes()}
+        parts = {"wire_bytes_per_rank": layer.wire_bytes(),
+                 "e2e_note": "per rank: 4 row chunks, h2d / compute+NCCL / d2h on three streams, steps double-buffered"}
         roof_bytes, roof_ms = None, None
         scaling = "strong"
 
@@ -352,15 +501,34 @@ def run_ours(args, n, e):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "breakdown": parts, "algorithmic_bytes_per_step": total_bytes,
     }
+    if parity is not None:
+        line["parity"] = parity
     if roof_bytes is not None:
         achieved = roof_bytes / (roof_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "spgemm_fwd_kernel<%d>" % k, "achieved": achieved, "peak": peak,
+        prof = ncu_traffic("%s_k%d" % (args.shape, k), None) or {}
+        gathered = e * (8 + 5 * k) + n * DIM * 4
+        line["roofline"] = {"bound": "hbm", "kernel": "spgemm_fwd_slots_kernel<%d, 2>" % k, "achieved": achieved, "peak": peak,
                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": roof_bytes, "ms_per_launch": roof_ms,
-                            "traffic": ncu_traffic("%s_k%d" % (args.shape, k), "spgemm_fwd_kernel"),
+                            "traffic": prof.get("spgemm_fwd_kernel"),
                             "layer_frac": value / peak,
                             "note": "not HBM-limited: the kernel saturates the SM LSU data pipe "
-                                    "(l1tex__data_pipe_lsu_wavefronts ~96% of peak), see profiles/ and DESIGN.md"}
+                                    "(l1tex__data_pipe_lsu_wavefronts ~91% of peak), see profiles/ and DESIGN.md",
+                            "l2": {"what": "the roofline this kernel is actually on: every edge gathers a 160-byte CBSR row "
+                                           "out of L2 and scatters 32 products into shared memory",
+                                   "gathered_bytes_per_launch": gathered,
+                                   "achieved_tbs": gathered / (roof_ms * 1e-3) / 1e12,
+                                   "peak_gather_tbs": L2_GATHER_PEAK_TBS, "peak_red_add_tbs": L2_RED_PEAK_TBS,
+                                   "frac_of_gather_peak": gathered / (roof_ms * 1e-3) / 1e12 / L2_GATHER_PEAK_TBS,
+                                   "lsu_wavefronts_per_edge": prof.get("fwd_lsu_wavefronts_per_edge"),
+                                   "smem_conflict_wavefronts_per_edge": prof.get("fwd_smem_conflicts_per_edge"),
+                                   "lsu_pipe_pct_of_peak": prof.get("fwd_lsu_pct_of_peak"),
+                                   "peaks_source": "tools/l2_bw.cu (profiles/r01_microbench_l2.txt); ncu figures from the "
+                                                   "committed capture named in profiles/roofline_traffic.json"}}
+    if sweep is not None:
+        line["extra"] = {"sweep": sweep,
+                         "sweep_note": "per-kernel ms (median of 5, CUDA events) and fraction of the measured HBM peak on "
+                                       "SURVEY 8(d) algorithmic bytes; ref_* = the reference's kernels on the same inputs and GPU"}
     if world == 1 and not args.no_cpu_baseline:
         leg = cpu_leg(n, e, k, seconds_budget=20.0, steps=1, warmup=0)
         line["cpu_baseline"] = {kk: leg[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
@@ -379,6 +547,9 @@ def main():
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--scale", type=float, default=1.0, help="developer knob: shrink the graph (not a contract bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check after the timed region")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the secondary configurations (extra.sweep)")
+    ap.add_argument("--kind", default="uniform", choices=["uniform", "powerlaw"], help="degree distribution of the synthetic graph")
     ap.add_argument("--bwd-mode", default="reduce_scatter", choices=["reduce_scatter", "allgather", "overlap"],
                     help="multi-GPU backward exchange (sharded.py)")
     ap.add_argument("--partition", default="rows", choices=["rows", "nnz"],

@@ -87,3 +87,89 @@ class HostStagedMaxKLayer:
         return done
 
     launches_per_call = property(lambda self: len(self.bounds) * 4)   # top-k + fwd + (bwd, long-row bwd) per slab
+
+
+class ShardedHostStagedLayer:
+    """The same three-stream slab pipeline for ONE RANK of the row-sharded layer (sharded.py): every GPU has its
+    own PCIe link, so each rank streams its row slab of the features / upstream gradient in and its slab of the
+    aggregate / sampled gradient out while it computes.
+
+        h2d stream : x chunk 0..S-1, then grad chunk 0..S-1
+        compute    : top-k(x chunk j) as its chunk lands -> all_gather of the rank's CBSR slab (NCCL, on this stream)
+                     forward SpGEMM over row chunk j -> out chunk j
+                     SSpMM over source-row chunk j as its gradient lands (accumulating into the full-size partial)
+                     reduce_scatter(sum) of the partial -> this rank's gs slab
+        d2h stream : out chunk j as soon as its forward finished, gs at the end
+    """
+
+    def __init__(self, layer, dim=256, slabs=4):
+        import torch.distributed as dist
+        self.dist = dist
+        self.layer = layer
+        rows = layer.rows
+        self.ip, self.ix, self.va = rows["indptr"], rows["indices"], rows["values"]
+        self.dev = self.ix.device
+        self.m, self.k, self.world, self.dim = layer.m, layer.k, layer.world, int(dim)
+        s = max(1, min(int(slabs), self.m))
+        step = (self.m + s - 1) // s
+        self.bounds = [(lo, min(lo + step, self.m)) for lo in range(0, self.m, step)]
+        self.plans = [K.build_plan(self.ip[lo:hi], self.ip[lo + 1:hi + 1]) for lo, hi in self.bounds]
+        self.h2d, self.comp, self.d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
+        mk = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=self.dev)
+        m, k, w = self.m, self.k, self.world
+        self.sets = [{"x": mk(m, dim), "g": mk(m, dim), "out": mk(m, dim), "gs": mk(m, k), "vals": mk(m, k),
+                      "sel": mk(m, k, dt=torch.uint8), "vals_full": mk(w * m, k), "sel_full": mk(w * m, k, dt=torch.uint8),
+                      "partial": mk(w * m, k), "done": None} for _ in range(2)]
+        self.calls = 0
+
+    def run(self, hx, hg, hout, hgs, block_current_stream=True):
+        """hx, hg: pinned [m, dim] host tensors (this rank's slab); hout [m, dim], hgs [m, k]: pinned host outputs."""
+        dist, group = self.dist, self.layer.group
+        b = self.sets[self.calls % 2]
+        self.calls += 1
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.h2d, self.comp, self.d2h):
+            s.wait_stream(cur)
+        if b["done"] is not None:
+            self.h2d.wait_event(b["done"])
+        ev = lambda: torch.cuda.Event()
+        ex, eg, ef = [ev() for _ in self.bounds], [ev() for _ in self.bounds], [ev() for _ in self.bounds]
+        with torch.cuda.stream(self.h2d):
+            for j, (lo, hi) in enumerate(self.bounds):
+                b["x"][lo:hi].copy_(hx[lo:hi], non_blocking=True)
+                ex[j].record(self.h2d)
+            for j, (lo, hi) in enumerate(self.bounds):
+                b["g"][lo:hi].copy_(hg[lo:hi], non_blocking=True)
+                eg[j].record(self.h2d)
+        with torch.cuda.stream(self.comp):
+            for j, (lo, hi) in enumerate(self.bounds):
+                self.comp.wait_event(ex[j])
+                K.topk_cbsr(b["x"][lo:hi], self.k, order=K.ORDER_BANKED, out_values=b["vals"][lo:hi], out_sel=b["sel"][lo:hi])
+            dist.all_gather_into_tensor(b["vals_full"], b["vals"], group=group)
+            dist.all_gather_into_tensor(b["sel_full"], b["sel"], group=group)
+            for j, (lo, hi) in enumerate(self.bounds):
+                K.spgemm_forward_csr(self.ip[lo:hi], self.ip[lo + 1:hi + 1], self.ix, self.va, b["vals_full"], b["sel_full"],
+                                     out_dim=self.dim, out=b["out"][lo:hi], plan=self.plans[j])
+                ef[j].record(self.comp)
+            b["partial"].zero_()
+            for j, (lo, hi) in enumerate(self.bounds):
+                self.comp.wait_event(eg[j])
+                K.sspmm_backward_csr(self.ip[lo:hi], self.ip[lo + 1:hi + 1], self.ix, self.va, b["g"][lo:hi], b["sel_full"],
+                                     out=b["partial"], accumulate=True)
+            dist.reduce_scatter_tensor(b["gs"], b["partial"], op=dist.ReduceOp.SUM, group=group)
+            e_bwd = ev()
+            e_bwd.record(self.comp)
+        with torch.cuda.stream(self.d2h):
+            for j, (lo, hi) in enumerate(self.bounds):
+                self.d2h.wait_event(ef[j])
+                hout[lo:hi].copy_(b["out"][lo:hi], non_blocking=True)
+            self.d2h.wait_event(e_bwd)
+            hgs.copy_(b["gs"], non_blocking=True)
+            done = ev()
+            done.record(self.d2h)
+        b["done"] = done
+        if block_current_stream:
+            cur.wait_event(done)
+        return done
+
+    launches_per_call = property(lambda self: len(self.bounds) * 4)
