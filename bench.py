@@ -176,7 +176,7 @@ def workload_config(args, n, e):
                         "hidden %d, k=%d: top-k + fwd SpGEMM + bwd SSpMM" % (args.shape, n, e, args.kind, DIM, args.k),
             "shape": args.shape, "nodes": n, "edges": e, "hidden": DIM, "k": args.k,
             "l2_note": "inputs per step (CSR 917 MB + features 239 MB + gradient 239 MB) exceed the 126 MB L2; no flush needed",
-            "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs (%s partition), all_gather(CBSR) fwd, %s bwd" % (args.gpus, "equal-row" if args.partition == "rows" else "equal-edge", args.bwd_mode)}
+            "parallelism": "1 GPU" if args.gpus == 1 else "1-D row sharding over %d GPUs (%s partition), CBSR slabs exchanged fwd (top-k writes into peer memory, else NCCL all_gather), %s bwd" % (args.gpus, "equal-row" if args.partition == "rows" else "equal-edge", args.bwd_mode)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -300,6 +300,8 @@ def run_ours(args, n, e):
     sampler = ClockSampler(nvml_index)
     parity = None
     sweep = None
+    from maxk_host_pipeline import bind_host_to_gpu
+    host_cores = bind_host_to_gpu(nvml_index) if world > 1 else 0     # pinned buffers land on the GPU's NUMA node
 
     if world == 1:
         ip = graph["indptr"]
@@ -399,7 +401,7 @@ def run_ours(args, n, e):
                 torch.cuda.empty_cache()
     else:
         from sharded import ShardedMaxKAggregation, _all_gather, padded_position
-        layer = ShardedMaxKAggregation(graph, k, backward_mode=args.bwd_mode, partition=args.partition)
+        layer = ShardedMaxKAggregation(graph, k, backward_mode=args.bwd_mode, partition=args.partition, gather=args.gather)
         m = layer.m
         x = torch.rand(m, DIM, device=dev, generator=torch.Generator(device=dev).manual_seed(123 + rank))
         grad = torch.rand(m, DIM, device=dev, generator=torch.Generator(device=dev).manual_seed(1123 + rank))
@@ -481,8 +483,10 @@ def run_ours(args, n, e):
         t_e2e = float(t.item())
         h2d, d2h = world * 2 * m * DIM * 4, world * (m * DIM * 4 + m * k * 4)
         launches = KERNELS_PER_STEP * args.steps * world
-        parts = {"wire_bytes_per_rank": layer.wire_bytes(),
-                 "e2e_note": "per rank: 4 row chunks, h2d / compute+NCCL / d2h on three streams, steps double-buffered"}
+        parts = {"wire_bytes_per_rank": layer.wire_bytes(), "forward_exchange": layer.gather,
+                 "forward_exchange_fallback_reason": layer.gather_error,
+                 "e2e_note": "per rank: 4 row chunks, h2d / compute+NCCL / d2h on three streams, steps double-buffered; "
+                             "process bound to the %d cores next to its GPU" % host_cores}
         roof_bytes, roof_ms = None, None
         scaling = "strong"
 
@@ -550,7 +554,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check after the timed region")
     ap.add_argument("--no-sweep", action="store_true", help="skip the secondary configurations (extra.sweep)")
     ap.add_argument("--kind", default="uniform", choices=["uniform", "powerlaw"], help="degree distribution of the synthetic graph")
-    ap.add_argument("--bwd-mode", default="reduce_scatter", choices=["reduce_scatter", "allgather", "overlap"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU forward exchange: top-k writing into peer memory, or NCCL all_gather")
+    ap.add_argument("--bwd-mode", default="reduce_scatter", choices=["reduce_scatter", "allgather"],
                     help="multi-GPU backward exchange (sharded.py)")
     ap.add_argument("--partition", default="rows", choices=["rows", "nnz"],
                     help="multi-GPU row partition: equal row slabs, or equal edge counts (identical on the uniform contract graph)")

@@ -82,6 +82,19 @@ int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
                    float *masked, maxk_stream_t stream);
 
 /*
+ * (1b) The same top-k for one rank's row slab of the row-sharded layer (the reference is single-GPU,
+ * all_train.py:224): row r of x becomes row (row_offset + r) of EVERY peer's gathered CBSR buffers
+ * peer_val[p] [P*m, k] / peer_sel[p] [P*m, k] (host arrays of n_peers <= MAXK_MAX_PEERS device pointers, the
+ * rank's own buffer included; peer-mapped memory, e.g. torch symmetric memory or cudaIpc mappings).  Replaces
+ * local top-k + two all_gather launches; the caller synchronises the ranks afterwards (one barrier).
+ * dim is 256, order MAXK_ORDER_BANKED, k in {8, 16, 32, 64, 96, 128}; x (and masked, nullable) 32-byte aligned.
+ */
+#define MAXK_MAX_PEERS 8
+int maxk_topk_cbsr_peers(const float *x, int64_t n_rows, int k, int n_peers,
+                         float *const *peer_val, uint8_t *const *peer_sel, int64_t row_offset,
+                         float *masked, maxk_stream_t stream);
+
+/*
  * (2) Forward row-wise-product SpGEMM: out = A_csr x scatter(CBSR)   (optionally / row_div).
  * Replaces spmm_kernel_opt2_sparse_v3_wrapper / spmm_maxk_forward
  * (cuda_kernel_wrappers.cu:38-56, cuda_kernel_bindings.cpp:42-104, kernels/spmm_maxk.cu:17-106).

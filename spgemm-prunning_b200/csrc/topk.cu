@@ -317,11 +317,20 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
 // entry is a prefix over the slots' ballots instead of a lane-group exchange; (value, column) pairs are
 // staged as one 8-byte shared-memory store; k is a template parameter.
 // ---------------------------------------------------------------------------------------------
+// Peer destinations of the row-sharded layer (sharded.py): the CBSR rows of this rank's slab are written
+// straight into every rank's gathered [P * m, k] buffers (peer-mapped symmetric memory over NVLink) instead
+// of a local store followed by two all_gather launches; the bytes on the wire are the same.
+struct PeerOut {
+    int n;                         // 0: plain local output
+    float *val[MAXK_MAX_PEERS];    // already offset to this rank's first row
+    uint8_t *sel[MAXK_MAX_PEERS];
+};
+
 template <int K>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restrict__ out_val,
                    uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32, int64_t *__restrict__ out_i64,
-                   float *__restrict__ masked, int one)
+                   float *__restrict__ masked, int one, const PeerOut peers)
 {
     __shared__ __align__(8) uint32_t s_ent[kTopkWarps][2 * K];   // (value bits, column id) pairs
     const int lane = lane_id();
@@ -439,8 +448,15 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
                 const uint2 ent = *reinterpret_cast<const uint2 *>(ent_w + 2 * i);
                 const int c = (int)ent.y;
                 const int64_t o = r * K + i;
-                out_val[o] = __uint_as_float(ent.x);
-                if (out_sel) out_sel[o] = (uint8_t)c;
+                if (peers.n == 0) {
+                    out_val[o] = __uint_as_float(ent.x);
+                    if (out_sel) out_sel[o] = (uint8_t)c;
+                } else {
+                    for (int p = 0; p < peers.n; ++p) {
+                        peers.val[p][o] = __uint_as_float(ent.x);
+                        peers.sel[p][o] = (uint8_t)c;
+                    }
+                }
                 if (out_i32) out_i32[o] = c;
                 if (out_i64) out_i64[o] = c;
             }
@@ -542,7 +558,8 @@ dense_spmm_kernel(const int *__restrict__ indptr, const int *__restrict__ idx, c
 // taken by the grid-stride loop, so that no SM idles while a partial second wave drains.
 template <int K>
 static cudaError_t launch_topk_banked(const float *x, int64_t n_rows, float *cbsr_val, uint8_t *cbsr_sel,
-                                      int32_t *idx_i32, int64_t *idx_i64, float *masked, cudaStream_t st)
+                                      int32_t *idx_i32, int64_t *idx_i64, float *masked, cudaStream_t st,
+                                      const PeerOut &peers)
 {
     static int resident[kMaxCachedDevices];    // CTAs per device, 0 = not queried yet
     int dev = 0;
@@ -558,8 +575,22 @@ static cudaError_t launch_topk_banked(const float *x, int64_t n_rows, float *cbs
     }
     const int64_t need = (n_rows + kTopkWarps - 1) / kTopkWarps;
     const int grid = (int)(need < cap ? need : cap);
-    topk_banked_kernel<K><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1);
+    topk_banked_kernel<K><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1, peers);
     return cudaGetLastError();
+}
+
+static cudaError_t dispatch_topk_banked(int k, const float *x, int64_t n_rows, float *cbsr_val, uint8_t *cbsr_sel,
+                                        int32_t *idx_i32, int64_t *idx_i64, float *masked, cudaStream_t st,
+                                        const PeerOut &peers)
+{
+    switch (k) {
+        case 8: return launch_topk_banked<8>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+        case 16: return launch_topk_banked<16>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+        case 32: return launch_topk_banked<32>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+        case 64: return launch_topk_banked<64>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+        case 96: return launch_topk_banked<96>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+        default: return launch_topk_banked<128>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+    }
 }
 
 static int grid_for_rows(int64_t n_rows)
@@ -595,16 +626,9 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     cudaStream_t st = (cudaStream_t)stream;
     if (dim == kAccDim && order == MAXK_ORDER_BANKED && bm >= 4 && !(((uintptr_t)x | (uintptr_t)masked) & 31)) {
         // the layer's hot configurations (32-byte loads need 32-byte aligned rows)
-        cudaError_t err;
-        switch (k) {
-            case 8: err = launch_topk_banked<8>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-            case 16: err = launch_topk_banked<16>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-            case 32: err = launch_topk_banked<32>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-            case 64: err = launch_topk_banked<64>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-            case 96: err = launch_topk_banked<96>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-            default: err = launch_topk_banked<128>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st); break;
-        }
-        return status_from_cuda(err);
+        PeerOut none;
+        none.n = 0;
+        return status_from_cuda(dispatch_topk_banked(k, x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, none));
     }
 #define MAXK_TOPK_LAUNCH(D256, ORD) \
     topk_cbsr_kernel<D256, ORD><<<grid, kTopkThreads, 0, st>>>(x, n_rows, dim, k, bm, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1)
@@ -619,6 +643,26 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     }
 #undef MAXK_TOPK_LAUNCH
     return status_from_cuda(cudaGetLastError());
+}
+
+extern "C" int maxk_topk_cbsr_peers(const float *x, int64_t n_rows, int k, int n_peers, float *const *peer_val,
+                                    uint8_t *const *peer_sel, int64_t row_offset, float *masked, maxk_stream_t stream)
+{
+    if (banked_modulus(k) < 4) return MAXK_ERR_BAD_K;
+    if (n_rows < 0 || row_offset < 0) return MAXK_ERR_SIZE;
+    if (n_peers < 1 || n_peers > MAXK_MAX_PEERS) return MAXK_ERR_SIZE;
+    if (n_rows == 0) return MAXK_OK;
+    if (!x || !peer_val || !peer_sel) return MAXK_ERR_NULL;
+    if (((uintptr_t)x | (uintptr_t)masked) & 31) return MAXK_ERR_ALIGN;
+    PeerOut peers;
+    peers.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_val[p] || !peer_sel[p]) return MAXK_ERR_NULL;
+        peers.val[p] = peer_val[p] + row_offset * k;
+        peers.sel[p] = peer_sel[p] + row_offset * k;
+    }
+    return status_from_cuda(dispatch_topk_banked(k, x, n_rows, nullptr, nullptr, nullptr, nullptr, masked,
+                                                 (cudaStream_t)stream, peers));
 }
 
 extern "C" int maxk_cbsr_scatter(const float *vals, const uint8_t *sel, int64_t n_rows, int dim, int k, float *dense,

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "maxk_status_string": (ctypes.c_char_p, [_c_int]),
     "maxk_banked_modulus": (_c_int, [_c_int]),
     "maxk_topk_cbsr": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "maxk_topk_cbsr_peers": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_i64, _c_ptr, _c_ptr]),
     "maxk_spgemm_forward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_int,
                                      _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_sspmm_backward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64,
@@ -337,6 +338,25 @@ def topk_cbsr(x, k, order=ORDER_BANKED, want_sel=True, want_i32=False, want_i64=
         _status(_lib.maxk_topk_cbsr(_ptr(x), n, d, k, order, _ptr(vals), _ptr(sel), _ptr(i32), _ptr(i64),
                                     _ptr(masked), _stream(x)), "maxk_topk_cbsr")
     return {"values": vals, "sel": sel, "i32": i32, "i64": i64, "masked": masked}
+
+
+MAX_PEERS = 8
+
+
+def topk_cbsr_to_peers(x, k, peer_val_ptrs, peer_sel_ptrs, row_offset, want_masked=False):
+    """Row-sharded top-k: row r of x -> row (row_offset + r) of every peer's gathered CBSR buffers (raw device
+    pointers of peer-mapped [P*m, k] fp32 / uint8 buffers, own rank included).  Returns the masked rows or None."""
+    x = _cuda(x, "input", torch.float32)
+    _check(x.dim() == 2 and x.size(1) == FULL_DIM, "the peer-writing top-k needs [rows, 256] features")
+    _check(len(peer_val_ptrs) == len(peer_sel_ptrs) and 1 <= len(peer_val_ptrs) <= MAX_PEERS, "1..8 peers")
+    n = x.size(0)
+    pv = (ctypes.c_void_p * len(peer_val_ptrs))(*[int(p) for p in peer_val_ptrs])
+    ps = (ctypes.c_void_p * len(peer_sel_ptrs))(*[int(p) for p in peer_sel_ptrs])
+    masked = torch.empty_like(x) if want_masked else None
+    with torch.cuda.device(x.device):
+        _status(_lib.maxk_topk_cbsr_peers(_ptr(x), n, int(k), len(peer_val_ptrs), pv, ps, int(row_offset), _ptr(masked),
+                                          _stream(x)), "maxk_topk_cbsr_peers")
+    return masked
 
 
 def cbsr_scatter(vals, sel, dim=FULL_DIM):

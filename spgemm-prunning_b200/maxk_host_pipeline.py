@@ -18,6 +18,28 @@ import torch
 import maxk_cuda_kernels as K
 
 
+def bind_host_to_gpu(nvml_index):
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity) BEFORE it allocates pinned host
+    buffers: first-touch places them on the GPU's NUMA node, so the host<->device copies of the pipeline do not
+    cross sockets (one process per GPU under torchrun is otherwise scheduled anywhere).  Returns the core count
+    it bound to, or 0 when NVML / sched_setaffinity is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(nvml_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 class HostStagedMaxKLayer:
     def __init__(self, indptr, indices, values, k, dim=256, slabs=8, device=None):
         self.dev = indices.device if device is None else device

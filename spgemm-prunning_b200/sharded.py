@@ -8,17 +8,17 @@ collective has uniform counts), the same rows of the features and of the output.
 forward   : local top-k -> CBSR slab [m, k]  --all_gather-->  CBSR of all N nodes
             -> local SpGEMM over the rank's rows (global column ids)          -> out [m, 256]
             5k bytes per node travel instead of 1 KiB (the point of the CBSR format).
+            On NCCL the gather is FUSED into the top-k kernel when torch symmetric memory is available
+            (gather="peer"): the kernel writes every CBSR row straight into all ranks' gathered buffers over
+            NVLink (maxk_topk_cbsr_peers) and one device-side barrier replaces the two all_gather launches.
+            Same bytes on the wire; falls back to all_gather (gather="nccl") where peer mapping is unavailable.
 backward  : "reduce_scatter" (default): every rank scatters the outer products of ITS rows into a
             full-size partial gs[N, k] (selectors of all nodes are resident since forward), then
             reduce_scatter(sum) -> gs [m, k].      N*k*4 bytes per rank on the wire.
             "allgather" (the variant BASELINE.json names): all_gather the dense gradient rows
             [m, 256] -> [N, 256], then SSpMM over the rank's COLUMN slice A[:, rows_p]; no reduction,
-            bit-reproducible, but 256/k times more bytes on the wire.
-            "overlap": same bytes as reduce_scatter, but the destinations are split into chunks of
-            consecutive owner ranks; the SSpMM of chunk c+1 runs while the partials of chunk c travel
-            (all_to_all on a second stream), and every owner sums the P blocks it received.  For
-            graphs whose partial gs is large (ogbn-products shape: 313 MB per rank) the collective
-            is as long as the kernel, so hiding it matters.
+            no cross-rank reduction (the SSpMM itself still accumulates with unordered fp32 atomics, so the
+            last bits vary run to run like on one GPU), but 256/k times more bytes on the wire.
 
 The collectives and the partition logic are backend-agnostic (the CPU tests run them on gloo with
 world_size 2); the compute backend defaults to the CUDA kernels and there is no CPU fallback in the
@@ -143,22 +143,6 @@ def _all_gather_pair(a, b, group):
     return out_a, out_b
 
 
-def split_rows_by_destination(rows, boundaries):
-    """Per-row edge positions of the destination boundaries: pos[j][r] = first edge of row r whose
-    column is >= boundaries[j].  Needs columns sorted inside every row (returns None otherwise)."""
-    indptr, indices = rows["indptr"].long(), rows["indices"].long()
-    m = indptr.numel() - 1
-    if indices.numel() == 0:
-        return [indptr[:-1].to(torch.int32).clone() for _ in boundaries]
-    n_pad = int(max(int(indices.max()) + 1, max(boundaries))) + 1
-    row_of = torch.repeat_interleave(torch.arange(m, device=indices.device), indptr[1:] - indptr[:-1])
-    keys = row_of * n_pad + indices
-    if bool((keys[1:] < keys[:-1]).any()):
-        return None
-    base = torch.arange(m, device=indices.device) * n_pad
-    return [torch.searchsorted(keys, base + int(b)).to(torch.int32) for b in boundaries]
-
-
 def _reduce_scatter_sum(full, group):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     m = full.size(0) // world
@@ -185,6 +169,15 @@ class CudaCompute:
         r = self.k.topk_cbsr(x, k, order=self.k.ORDER_BANKED)
         return r["values"], r["sel"]
 
+    def topk_masked(self, x, k):
+        """(values, selectors, x with every non-selected entry zeroed) in one pass."""
+        r = self.k.topk_cbsr(x, k, order=self.k.ORDER_BANKED, want_masked=True)
+        return r["values"], r["sel"], r["masked"]
+
+    def mask_apply(self, dense, sel, add_vals):
+        """dense * mask(sel) + scatter(add_vals): the MaxK backward plus the aggregation gradient, one kernel."""
+        return self.k.mask_apply(dense, sel, add_vals=add_vals)
+
     def spgemm(self, g, vals, sel, row_div=None):
         ip = g["indptr"]
         if g.get("plan") is None:                 # the slab's row plan, built once
@@ -196,19 +189,39 @@ class CudaCompute:
         ip = g["indptr"]
         return self.k.sspmm_backward_csr(ip[:-1], ip[1:], g["indices"], g["values"], grad, sel, row_div=row_div)
 
-    def sspmm_ranges(self, g, grad, sel, row_div, out):
-        """out += SSpMM over the per-row edge ranges [g['begin'], g['end'])."""
-        self.k.sspmm_backward_csr(g["begin"], g["end"], g["indices"], g["values"], grad, sel, row_div=row_div,
-                                  out=out, accumulate=True)
+
+class PeerGather:
+    """Gathered CBSR buffers [P*m, k] in torch symmetric memory (peer-mapped over NVLink), two sets: step s uses
+    set s % 2.  One barrier per step (after the peer writes) is enough: a rank can only be one barrier ahead of
+    the slowest one, so nobody writes set s % 2 again before every rank has finished reading it."""
+
+    def __init__(self, rows_total, k, device, group):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.sets = []
+        for _ in range(2):
+            vals = symm.empty((rows_total, k), dtype=torch.float32, device=device)
+            sel = symm.empty((rows_total, k), dtype=torch.uint8, device=device)
+            hv, hs = symm.rendezvous(vals, pg), symm.rendezvous(sel, pg)
+            self.sets.append({"vals": vals, "sel": sel, "hv": hv, "hs": hs,
+                              "val_ptrs": list(hv.buffer_ptrs), "sel_ptrs": list(hs.buffer_ptrs)})
+        self.step = 0
+
+    def next_set(self):
+        s = self.sets[self.step % 2]
+        self.step += 1
+        return s
 
 
 class ShardedMaxKAggregation:
     """top-k -> all_gather(CBSR) -> SpGEMM, and its backward, for one rank's row slab."""
 
     def __init__(self, graph, k, group=None, backward_mode="reduce_scatter", compute=None, row_div=None,
-                 overlap_chunks=4, partition="rows"):
-        if backward_mode not in ("reduce_scatter", "allgather", "overlap"):
-            raise ValueError("backward_mode must be 'reduce_scatter', 'allgather' or 'overlap'")
+                 partition="rows", gather="auto"):
+        if backward_mode not in ("reduce_scatter", "allgather"):
+            raise ValueError("backward_mode must be 'reduce_scatter' or 'allgather'")
+        if gather not in ("auto", "peer", "nccl"):
+            raise ValueError("gather must be 'auto', 'peer' (top-k writes into peer memory) or 'nccl' (all_gather)")
         if partition not in ("rows", "nnz"):
             raise ValueError("partition must be 'rows' (equal row slabs) or 'nnz' (equal edge counts)")
         self.group = group
@@ -231,17 +244,20 @@ class ShardedMaxKAggregation:
             self.row_div = torch.ones(self.m, dtype=torch.float32, device=row_div.device)
             self.row_div[: hi - lo] = row_div[lo:hi]
         self.sel_full = None
-        self.chunks = None
-        if backward_mode == "overlap":
-            n_chunks = max(1, min(int(overlap_chunks), self.world))
-            owners = [list(range(c * self.world // n_chunks, (c + 1) * self.world // n_chunks)) for c in range(n_chunks)]
-            bounds = [o[0] * self.m for o in owners] + [self.world * self.m]
-            pos = split_rows_by_destination(self.rows, bounds)
-            if pos is None:                      # unsorted columns: the chunks are not contiguous edge ranges
-                self.backward_mode = "reduce_scatter"
-            else:
-                self.chunks = [{"owners": o, "begin": pos[c], "end": pos[c + 1]} for c, o in enumerate(owners)]
-                self.comm_stream = torch.cuda.Stream() if self.rows["indices"].is_cuda else None
+        # forward exchange: fused into the top-k kernel over peer-mapped memory when possible
+        self.peer = None
+        self.gather_error = None
+        cuda_nccl = isinstance(self.compute, CudaCompute) and self.rows["indices"].is_cuda and \
+            dist.get_backend(group) == "nccl" and self.world <= self.compute.k.MAX_PEERS and \
+            self.compute.k._lib.maxk_banked_modulus(self.k) >= 4
+        if gather != "nccl" and cuda_nccl and os.environ.get("MAXK_PEER_GATHER", "1") == "1":
+            try:
+                self.peer = PeerGather(self.world * self.m, self.k, self.rows["indices"].device, group)
+            except Exception as ex:          # no peer mapping on this system: NCCL all_gather does the same job
+                self.gather_error = repr(ex)[:300]
+                if gather == "peer":
+                    raise
+        self.gather = "peer" if self.peer is not None else "nccl"
 
     def local_slab(self, full):
         """This rank's rows of a full [N, ...] tensor, zero-padded to the slab height m."""
@@ -254,10 +270,27 @@ class ShardedMaxKAggregation:
         """Number of real (non-padding) rows of this rank's slab."""
         return self.rows["row_hi"] - self.rows["row_lo"]
 
+    def gather_cbsr(self, x_local, want_masked=False):
+        """top-k of this rank's slab + exchange -> (vals_full [P*m, k], sel_full [P*m, k], masked slab or None)."""
+        if self.peer is not None and x_local.size(1) == 256:
+            st = self.peer.next_set()
+            masked = self.compute.k.topk_cbsr_to_peers(x_local, self.k, st["val_ptrs"], st["sel_ptrs"],
+                                                       row_offset=self.rank * self.m, want_masked=want_masked)
+            st["hv"].barrier(channel=0)          # every rank's rows have landed in every rank's buffers
+            return st["vals"], st["sel"], masked
+        masked = None
+        if want_masked and hasattr(self.compute, "topk_masked"):
+            vals, sel, masked = self.compute.topk_masked(x_local, self.k)
+        else:
+            vals, sel = self.compute.topk(x_local, self.k)
+            if want_masked:                      # injected test backends: plain torch
+                masked = torch.zeros_like(x_local).scatter_(1, sel.long(), vals)
+        vals_full, sel_full = _all_gather_pair(vals, sel, self.group)
+        return vals_full, sel_full, masked
+
     # x_local: [m, 256] (rows past the end of the slab are padding and may hold anything finite)
     def forward(self, x_local):
-        vals, sel = self.compute.topk(x_local, self.k)
-        vals_full, self.sel_full = _all_gather_pair(vals, sel, self.group)
+        vals_full, self.sel_full, _ = self.gather_cbsr(x_local)
         return self.compute.spgemm(self.rows, vals_full, self.sel_full, self.row_div)
 
     def backward(self, grad_local):
@@ -266,43 +299,10 @@ class ShardedMaxKAggregation:
         if self.backward_mode == "reduce_scatter":
             partial = self.compute.sspmm(self.rows, grad_local, self.sel_full, self.row_div)   # [P*m, k]
             return _reduce_scatter_sum(partial, self.group)
-        if self.backward_mode == "overlap":
-            return self._backward_overlap(grad_local)
         grad = grad_local if self.row_div is None else grad_local / self.row_div.unsqueeze(-1)
         grad_full = _all_gather(grad, self.group)                                             # [P*m, 256]
         lo = self.rank * self.m
         return self.compute.sspmm(self.cols, grad_full, self.sel_full[lo:lo + self.m].contiguous())
-
-    def _backward_overlap(self, grad_local):
-        """Chunked SSpMM + all_to_all: the partials of chunk c travel while chunk c+1 is computed."""
-        world, m, k = self.world, self.m, self.k
-        partial = torch.zeros(world * m, k, dtype=torch.float32, device=grad_local.device)
-        recv = torch.empty(world * m, k, dtype=torch.float32, device=grad_local.device)
-        cuda = grad_local.is_cuda
-        main = torch.cuda.current_stream() if cuda else None
-        if cuda:
-            self.comm_stream.wait_stream(main)
-        for ch in self.chunks:
-            sub = {"indptr": None, "begin": ch["begin"], "end": ch["end"], "indices": self.rows["indices"],
-                   "values": self.rows["values"]}
-            self.compute.sspmm_ranges(sub, grad_local, self.sel_full, self.row_div, partial)
-            lo, hi = ch["owners"][0] * m, (ch["owners"][-1] + 1) * m
-            in_split = [m if r in ch["owners"] else 0 for r in range(world)]
-            out_split = [m] * world if self.rank in ch["owners"] else [0] * world
-            out_buf = recv if self.rank in ch["owners"] else recv[:0]
-            if cuda:
-                done = torch.cuda.Event()
-                done.record(main)
-                with torch.cuda.stream(self.comm_stream):
-                    self.comm_stream.wait_event(done)
-                    dist.all_to_all_single(out_buf, partial[lo:hi], out_split, in_split, group=self.group)
-            else:
-                dist.all_to_all_single(out_buf, partial[lo:hi], out_split, in_split, group=self.group)
-        if cuda:
-            main.wait_stream(self.comm_stream)
-            partial.record_stream(self.comm_stream)
-            recv.record_stream(self.comm_stream)
-        return recv.view(world, m, k).sum(dim=0)
 
     def wire_bytes(self):
         """Bytes each rank RECEIVES per forward / backward (for the report)."""
@@ -318,10 +318,10 @@ class _ShardedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_local, layer):
-        vals, sel = layer.compute.topk(x_local, layer.k)
-        vals_full, sel_full = _all_gather_pair(vals, sel, layer.group)
+        vals_full, sel_full, masked = layer.gather_cbsr(x_local, want_masked=True)
         out = layer.compute.spgemm(layer.rows, vals_full, sel_full, layer.row_div)
-        masked = torch.zeros_like(x_local).scatter_(1, sel.long(), vals)
+        if layer.peer is not None:
+            sel_full = sel_full.clone()          # the peer buffers are recycled two steps later; autograd keeps its own
         ctx.layer = layer
         ctx.save_for_backward(sel_full)
         layer.sel_full = sel_full
@@ -335,6 +335,8 @@ class _ShardedFn(torch.autograd.Function):
         sel_local = sel_full[lo:lo + layer.m].contiguous()
         layer.sel_full = sel_full
         gs = layer.backward(grad_out.contiguous())
+        if hasattr(layer.compute, "mask_apply"):              # grad * mask + scatter(gs) in one kernel
+            return layer.compute.mask_apply(grad_masked.contiguous(), sel_local, gs), None
         dense = torch.zeros(gs.size(0), grad_masked.size(1), dtype=gs.dtype, device=gs.device)
         dense.scatter_(1, sel_local.long(), gs)
         mask = torch.zeros_like(grad_masked).scatter_(1, sel_local.long(), 1.0)

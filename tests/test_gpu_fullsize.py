@@ -77,3 +77,55 @@ def test_fullsize_warp4_roundtrip(reddit):
     assert int(q[:, 2].sum()) == g["e_num"] and int(q[:, 2].max()) <= 64 and int(q[:, 3].abs().max()) == 0
     rows = kern._rows_from_warp4(w4, nw, g["v_num"])
     assert torch.equal(rows[0], ip[:-1]) and torch.equal(rows[1], ip[1:])          # uniform graph: no empty rows
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sampled-row ORACLE parity at the full size of every BASELINE.json shape: 1024 random output rows / 1024
+# random destination rows per case are recomputed by the C oracle on the sub-problem they span
+# (oracle/sampled_parity.py).  Tolerance: index sets bit-exact, |got - exp| <= 1e-6 + 1e-5 |exp|.
+# ---------------------------------------------------------------------------------------------------------
+FULL_CASES = [("flickr", "uniform", 32), ("reddit", "uniform", 8), ("reddit", "uniform", 16), ("reddit", "uniform", 32),
+              ("reddit", "uniform", 64), ("reddit", "powerlaw", 32), ("yelp", "uniform", 32), ("proteins", "uniform", 64),
+              ("products", "uniform", 32)]
+_graphs = {}
+
+
+def _full_graph(shape, kind):
+    from synth_graphs import SHAPES, synth_graph
+    key = (shape, kind)
+    if key not in _graphs:
+        _graphs.clear()                                  # one full-size graph resident at a time
+        torch.cuda.empty_cache()
+        n, e = SHAPES[shape]
+        _graphs[key] = synth_graph(n, e, seed=123, kind=kind, device="cuda")
+    return _graphs[key]
+
+
+@pytest.mark.parametrize("shape,kind,k", FULL_CASES)
+def test_fullsize_sampled_rows_match_the_oracle(shape, kind, k):
+    import maxk_cuda_kernels as kern
+    import sampled_parity as sp
+    g = _full_graph(shape, kind)
+    n = g["v_num"]
+    ip, ix, va = g["indptr"], g["indices"], g["values"]
+    rb, re_ = ip[:-1], ip[1:]
+    gen = torch.Generator(device="cuda").manual_seed(k)
+    x = torch.randn(n, 256, device="cuda", generator=gen)            # signed features: negatives must survive
+    grad = torch.rand(n, 256, device="cuda", generator=gen)
+    deg = (re_ - rb).clamp(min=1).float()
+    r = kern.topk_cbsr(x, k, order=kern.ORDER_BANKED)
+    plan = kern.build_plan(rb, re_)
+    out = kern.spgemm_forward_csr(rb, re_, ix, va, r["values"], r["sel"], row_div=deg, plan=plan)
+    gs = kern.sspmm_backward_csr(rb, re_, ix, va, grad, r["sel"], row_div=deg)
+    rows = sp.sample_ids(n, 1024, seed=1, device="cuda")
+    sets_equal, vals_equal = sp.check_topk(x[rows], r["values"][rows], r["sel"][rows], k)
+    assert sets_equal and vals_equal
+    fv, fr = sp.check_forward(ip, ix, va, r["values"], r["sel"], rows, out[rows], row_div=deg)
+    assert fv <= 1.0, "forward: violation %.3f (max rel %.3e)" % (fv, fr)
+    dst = sp.sample_ids(n, 1024, seed=2, device="cuda")
+    bv, br, used = sp.check_backward(ip, ix, va, grad, r["sel"], dst, gs[dst], row_div=deg)
+    assert used > 0 and bv <= 1.0, "backward: violation %.3f (max rel %.3e)" % (bv, br)
+    # the un-planned entry point (plan rebuilt inside the call) gives the same rows bit for bit
+    assert torch.equal(out, kern.spgemm_forward_csr(rb, re_, ix, va, r["values"], r["sel"], row_div=deg))
+    h = plan.header()
+    assert h["n_rows"] == n and h["long_rows"] == int(((re_ - rb) >= 4096).sum())

@@ -34,16 +34,6 @@ class OracleCompute:
                               deg=None if row_div is None else row_div.numpy())
         return torch.from_numpy(gs)
 
-    def sspmm_ranges(self, g, grad, sel, row_div, out):
-        """out += SSpMM over per-row edge ranges: the ranges are compacted into a CSR for the oracle."""
-        b, e = g["begin"].numpy().astype(np.int64), g["end"].numpy().astype(np.int64)
-        ptr = np.zeros(len(b) + 1, np.int32)
-        ptr[1:] = np.cumsum(e - b)
-        pick = np.concatenate([np.arange(lo, hi) for lo, hi in zip(b, e)]) if ptr[-1] else np.zeros(0, np.int64)
-        gs = oracle.sspmm_bwd(ptr, g["indices"].numpy()[pick], g["values"].numpy()[pick], grad.numpy(), sel.numpy(),
-                              deg=None if row_div is None else row_div.numpy())
-        out += torch.from_numpy(gs)
-
 
 def _free_port():
     with socket.socket() as s:
@@ -78,8 +68,7 @@ def _worker(rank, world, port, mode, use_div, result_dir, partition="rows"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,use_div", [("reduce_scatter", False), ("reduce_scatter", True), ("allgather", True),
-                                          ("overlap", True)])
+@pytest.mark.parametrize("mode,use_div", [("reduce_scatter", False), ("reduce_scatter", True), ("allgather", True)])
 def test_sharded_layer_matches_single_process_oracle(tmp_path, mode, use_div):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), mode, use_div, str(tmp_path)), nprocs=world, join=True)
@@ -102,7 +91,7 @@ def test_sharded_layer_matches_single_process_oracle(tmp_path, mode, use_div):
         assert int(r["wire_bwd"]) == (m * 256 * 4 if mode == "allgather" else m * k * 4)
 
 
-@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather", "overlap"])
+@pytest.mark.parametrize("mode", ["reduce_scatter", "allgather"])
 def test_edge_balanced_partition_matches_single_process_oracle(tmp_path, mode):
     """partition="nnz": slab boundaries from the prefix sum of the degrees, slabs padded to a common height,
     column ids remapped into the padded numbering -- same results as the single-process oracle, and the
