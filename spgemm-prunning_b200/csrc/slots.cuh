@@ -25,7 +25,7 @@ namespace maxk {
 constexpr int kSL = 4;                      // lanes per slot == banks per copy
 constexpr int kSS = 32 / kSL;               // slots per warp
 constexpr int kSW = 16;                     // steps per CSR window
-constexpr int kCwStride = kSW + 1;          // padded window row: 8 slots read 8 different bank pairs
+constexpr int kCwStride = 2 * kSW + 1;      // padded ring row (2 windows): 8 slots read 8 different bank pairs
 constexpr int kCwEntries = kSS * kCwStride; // int2 entries per warp (>= kSS * kSW for the shared mode)
 constexpr int kSlotCopyWords = kSS * kAccDim;                                   // 2048 floats per warp
 constexpr size_t kSlotWarpBytes = kSlotCopyWords * sizeof(float) + kCwEntries * sizeof(int2);
@@ -103,13 +103,25 @@ __device__ __forceinline__ Desc load_desc(const PlanView &p, const Item &it, int
     return d;
 }
 
-// CSR window of one item: which (index, value) pair a lane fetches for fill instruction i (4 per window)
-// and where it parks it in the shared-memory window.
+// CSR windows of one item.  Window w of a slot holds 16 consecutive (index, value) pairs; fill instruction i
+// (4 per window) fetches the windows of slots 2i and 2i+1, one half-warp each, and parks them in a two-window
+// ring per slot in shared memory.
+//   * short items: window w = the slot's edges [b + 16 w, b + 16 w + 16); neighbouring rows of a regular
+//     low-degree graph are contiguous in the CSR arrays, so the 8 windows of a warp share their sectors;
+//   * long items ("aligned", >= kAlignedSteps steps): windows start at multiples of 16 entries (64 bytes), the
+//     DRAM access granularity -- un-aligned 64-byte windows made every 64-byte chunk of the CSR arrays cross
+//     the DRAM bus twice (ncu, Reddit shape: 1.63 GB read against 1.0 GB of operands).  A slot then reads its
+//     step s at ring entry (b % 16 + s) % 32 and needs windows j and j+1 parked during block j (lead = 1);
+//   * shared items: one row, 128 consecutive edges per 16 steps, flat (slot q, step s) -> entry 8 s + q.
+constexpr int kAlignedSteps = 64;
+constexpr int kRing = 2 * kSW;              // ring entries per slot
 struct WindowMap {
-    int base[kSS / 2];   // edge position fetched for step 0
-    int lim[kSS / 2];    // first edge position past the slot's (or row's) range
-    int wi0, wis;        // window entry written by fill instruction i: wi0 + i * wis
-    int mult;            // edge positions per step (1 separate, 8 shared)
+    int base[kSS / 2];   // edge position fetched for window 0
+    int wi0, wis;        // window entry written by fill instruction i: wi0 + i * wis (+ ring offset of the window)
+    int mult;            // edge positions per window (16 separate, 128 shared)
+    int ring;            // ring offset of odd windows (16 separate, 0 shared)
+    int lead;            // windows that must be parked ahead of the block being processed (1 aligned, else 0)
+    int n_win;           // windows of the item
 };
 __device__ __forceinline__ WindowMap make_window_map(const Desc &d, int shared, int lane)
 {
@@ -118,58 +130,80 @@ __device__ __forceinline__ WindowMap make_window_map(const Desc &d, int shared, 
     if (shared) {
         const int b0 = __shfl_sync(kFullMask, d.b, 0), e0 = __shfl_sync(kFullMask, d.e, 0);
 #pragma unroll
-        for (int i = 0; i < kSS / 2; ++i) {
-            m.base[i] = b0 + 32 * i + lane;
-            m.lim[i] = e0;
-        }
+        for (int i = 0; i < kSS / 2; ++i) m.base[i] = b0 + 32 * i + lane;
         m.wi0 = lane;
         m.wis = 32;
-        m.mult = kSS;
+        m.mult = kSS * kSW;
+        m.ring = 0;
+        m.lead = 0;
+        m.n_win = ((e0 - b0 + kSS - 1) / kSS + kSW - 1) / kSW;
     } else {
+        const int steps = __reduce_max_sync(kFullMask, d.e - d.b);
+        const int aligned = steps >= kAlignedSteps;
 #pragma unroll
         for (int i = 0; i < kSS / 2; ++i) {
-            const int slot = 2 * i + half;
-            const int wb = __shfl_sync(kFullMask, d.b, slot), we = __shfl_sync(kFullMask, d.e, slot);
-            m.base[i] = wb + l16;
-            m.lim[i] = we;
+            const int wb = __shfl_sync(kFullMask, d.b, 2 * i + half);
+            m.base[i] = (aligned ? (wb & ~(kSW - 1)) : wb) + l16;
         }
         m.wi0 = half * kCwStride + l16;
         m.wis = 2 * kCwStride;
-        m.mult = 1;
+        m.mult = kSW;
+        m.ring = kSW;
+        m.lead = aligned;
+        m.n_win = (steps + (kSW - 1) * (1 + aligned)) / kSW;
     }
     return m;
 }
 
-// fetch the window that starts at step s0 (register-resident until it is parked)
+// Window loads bypass L1 but carry NO evict-first hint: a 64-byte window is half of a 128-byte L2 line and
+// the other half is wanted 16 steps later.
+__device__ __forceinline__ int ld_window_i32(const int *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_window_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// fetch window w (register-resident until it is parked); positions past the edge arrays are skipped, positions
+// past the slot's own row are fetched and never read
 __device__ __forceinline__ void fetch_window(const WindowMap &m, const int *__restrict__ idx,
-                                             const float *__restrict__ val, int s0, int (&pc)[kSS / 2],
+                                             const float *__restrict__ val, int w, int n_edges, int (&pc)[kSS / 2],
                                              float (&pw)[kSS / 2])
 {
 #pragma unroll
     for (int i = 0; i < kSS / 2; ++i) {
-        const int a = m.base[i] + s0 * m.mult;
+        const int a = m.base[i] + w * m.mult;
         pc[i] = 0;
         pw[i] = 0.f;
-        if (a < m.lim[i]) {
-            pc[i] = ld_stream_i32(idx + a);
-            pw[i] = ld_stream_f32(val + a);
+        if (a < n_edges) {
+            pc[i] = ld_window_i32(idx + a);
+            pw[i] = ld_window_f32(val + a);
         }
     }
 }
 
-__device__ __forceinline__ void park_window(const WindowMap &m, int2 *cw, const int (&pc)[kSS / 2],
+__device__ __forceinline__ void park_window(const WindowMap &m, int2 *cw, int w, const int (&pc)[kSS / 2],
                                             const float (&pw)[kSS / 2])
 {
+    const int off = m.wi0 + (w & 1) * m.ring;
 #pragma unroll
-    for (int i = 0; i < kSS / 2; ++i) cw[m.wi0 + i * m.wis] = make_int2(pc[i], __float_as_int(pw[i]));
+    for (int i = 0; i < kSS / 2; ++i) cw[off + i * m.wis] = make_int2(pc[i], __float_as_int(pw[i]));
 }
 
 // per-lane view of its slot inside an item
 struct SlotView {
     int cnt;        // steps this slot works
     int steps;      // steps of the item (max over slots)
-    int rd_base;    // window entry of step 0
-    int rd_stride;  // window entries per step
+    int rd_base;    // window entry of ring position 0
+    int rd_stride;  // window entries per ring position
+    int rd_mask;    // ring positions - 1
+    int rd_off;     // ring position of step 0
 };
 __device__ __forceinline__ SlotView make_slot_view(const Desc &d, int shared, int lane)
 {
@@ -181,14 +215,22 @@ __device__ __forceinline__ SlotView make_slot_view(const Desc &d, int shared, in
         s.steps = (len + kSS - 1) / kSS;
         s.rd_base = q;
         s.rd_stride = kSS;
+        s.rd_mask = kSW - 1;
+        s.rd_off = 0;
     } else {
         const int len = d.e - d.b;                       // lanes >= 8 hold 0
         s.cnt = __shfl_sync(kFullMask, len, q);
         s.steps = __reduce_max_sync(kFullMask, len);
         s.rd_base = q * kCwStride;
         s.rd_stride = 1;
+        s.rd_mask = kRing - 1;
+        s.rd_off = s.steps >= kAlignedSteps ? (__shfl_sync(kFullMask, d.b, q) & (kSW - 1)) : 0;
     }
     return s;
+}
+__device__ __forceinline__ int2 read_window(const SlotView &s, const int2 *cw, int step)
+{
+    return cw[s.rd_base + ((s.rd_off + step) & s.rd_mask) * s.rd_stride];
 }
 
 // word offset of column c inside a slot copy (add 4 * slot)
@@ -197,14 +239,14 @@ __device__ __forceinline__ int slot_word(int c) { return ((c & 0xfc) << 3) | (c 
 // 32-byte / 8-byte loads of re-used operands (kept in L2)
 __device__ __forceinline__ void ld_keep_f32x8(const float *p, float *v, uint64_t pol)
 {
-    asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p), "l"(pol));
 }
 __device__ __forceinline__ uint2 ld_keep_u32x2(const void *p, uint64_t pol)
 {
     uint2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
 }
 

@@ -59,7 +59,7 @@ template <int K, int MINB>
 __global__ void __launch_bounds__(kFsThreads, MINB)
 spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ idx, const float *__restrict__ val,
                         const float *__restrict__ cval, const uint8_t *__restrict__ csel, float *__restrict__ out,
-                        int dim, int k, const float *__restrict__ row_div)
+                        int n_edges, int dim, int k, const float *__restrict__ row_div)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -92,7 +92,7 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
     int pc[kSS / 2];
     float pw[kSS / 2];
     WindowMap wm = make_window_map(d_cur, it_cur.shared, lane);
-    fetch_window(wm, idx, val, 0, pc, pw);
+    fetch_window(wm, idx, val, 0, n_edges, pc, pw);
 
     for (;;) {
         const SlotView sv = make_slot_view(d_cur, it_cur.shared, lane);
@@ -104,18 +104,26 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
             d_nxt2 = load_desc(pv, it, lane);
             sh_nxt2 = it.shared;
         }
+        // the registers pc/pw always hold the next window to park: window `parked` of this item, or, once all
+        // of them are parked, window 0 of the next item
+        const int n_win = wm.n_win, lead = wm.lead;
+        int parked = 0;
         bool next_fetched = false;
-        for (int s0 = 0; s0 < sv.steps; s0 += kSW) {
-            __syncwarp();
-            park_window(wm, cw, pc, pw);
-            __syncwarp();
-            if (s0 + kSW < sv.steps) {
-                fetch_window(wm, idx, val, s0 + kSW, pc, pw);
-            } else if (has_nxt) {
-                wm = make_window_map(d_nxt, sh_nxt, lane);
-                fetch_window(wm, idx, val, 0, pc, pw);
-                next_fetched = true;
+        int j_blk = 0;
+        for (int s0 = 0; s0 < sv.steps; s0 += kSW, ++j_blk) {
+            while (parked <= j_blk + lead && parked < n_win) {
+                __syncwarp();
+                park_window(wm, cw, parked, pc, pw);
+                ++parked;
+                if (parked < n_win) {
+                    fetch_window(wm, idx, val, parked, n_edges, pc, pw);
+                } else if (has_nxt) {
+                    const WindowMap wn = make_window_map(d_nxt, sh_nxt, lane);
+                    fetch_window(wn, idx, val, 0, n_edges, pc, pw);
+                    next_fetched = true;
+                }
             }
+            __syncwarp();
             const int nj = min(kSW, sv.steps - s0);
             if constexpr (K != 0) {
                 constexpr int U = FwdTune<K, MINB>::UNROLL;
@@ -125,7 +133,7 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
                     bool ok[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int2 e = cw[sv.rd_base + (j + u) * sv.rd_stride];
+                        const int2 e = read_window(sv, cw, s0 + j + u);
                         w[u] = __int_as_float(e.y);
                         ok[u] = s0 + j + u < sv.cnt;
                         if (ok[u]) {
@@ -142,16 +150,17 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
                 }
             } else {
                 for (int j = 0; j < nj; ++j) {
-                    const int2 e = cw[sv.rd_base + j * sv.rd_stride];
+                    const int2 e = read_window(sv, cw, s0 + j);
                     if (s0 + j < sv.cnt) accumulate_any_k(cval, csel, (size_t)e.x * k, k, t, __int_as_float(e.y), acc_q);
                     __syncwarp();
                 }
             }
         }
         if (has_nxt && !next_fetched) {               // an item without edges
-            wm = make_window_map(d_nxt, sh_nxt, lane);
-            fetch_window(wm, idx, val, 0, pc, pw);
+            const WindowMap wn = make_window_map(d_nxt, sh_nxt, lane);
+            fetch_window(wn, idx, val, 0, n_edges, pc, pw);
         }
+        if (has_nxt) wm = make_window_map(d_nxt, sh_nxt, lane);
         __syncwarp();
 
         // ---- epilogue: write the rows of this item, re-zero the copies ---------------------------------
@@ -227,7 +236,7 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
 
 template <int K, int MINB>
 static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const float *val, const float *cval,
-                                      const uint8_t *csel, float *out, int dim, int k, const float *row_div,
+                                      const uint8_t *csel, float *out, int n_edges, int dim, int k, const float *row_div,
                                       cudaStream_t stream)
 {
     const size_t smem = (size_t)kFsWarps * kSlotWarpBytes;
@@ -248,7 +257,7 @@ static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const flo
         cfg.configured = true;
     }
     spgemm_fwd_slots_kernel<K, MINB><<<cfg.sms * cfg.blocks_per_sm, kFsThreads, smem, stream>>>(plan, idx, val, cval, csel,
-                                                                                                out, dim, k, row_div);
+                                                                                                out, n_edges, dim, k, row_div);
     return cudaGetLastError();
 }
 
@@ -257,10 +266,10 @@ static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const flo
 // against 2.62 ms, ogbn-products shape 4.2 ms against 2.6 ms; profiles/r02_slots_lab.txt).
 template <int K>
 static cudaError_t launch_fwd_slots(const int *plan, const int *idx, const float *val, const float *cval,
-                                    const uint8_t *csel, float *out, int dim, int k, const float *row_div,
+                                    const uint8_t *csel, float *out, int n_edges, int dim, int k, const float *row_div,
                                     cudaStream_t stream)
 {
-    return launch_fwd_slots_b<K, 2>(plan, idx, val, cval, csel, out, dim, k, row_div, stream);
+    return launch_fwd_slots_b<K, 2>(plan, idx, val, cval, csel, out, n_edges, dim, k, row_div, stream);
 }
 
 }  // namespace maxk
@@ -286,13 +295,13 @@ extern "C" int maxk_spgemm_forward_planned(const void *plan, const int32_t *indi
     const int *p = reinterpret_cast<const int *>(plan);
     cudaError_t err;
     switch (fast ? k : 0) {
-        case 8: err = launch_fwd_slots<8>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
-        case 16: err = launch_fwd_slots<16>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
-        case 32: err = launch_fwd_slots<32>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
-        case 64: err = launch_fwd_slots<64>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
-        case 96: err = launch_fwd_slots<96>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
-        case 128: err = launch_fwd_slots<128>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
-        default: err = launch_fwd_slots<0>(p, indices, values, cbsr_val, cbsr_sel, out, dim, k, row_div, stream); break;
+        case 8: err = launch_fwd_slots<8>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        case 16: err = launch_fwd_slots<16>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        case 32: err = launch_fwd_slots<32>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        case 64: err = launch_fwd_slots<64>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        case 96: err = launch_fwd_slots<96>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        case 128: err = launch_fwd_slots<128>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        default: err = launch_fwd_slots<0>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
     }
     return status_from_cuda(err);
 }
