@@ -112,7 +112,9 @@ int maxk_topk_cbsr_peers(const float *x, int64_t n_rows, int k, int n_peers,
  * maxk_spgemm_forward builds the plan into the workspace on every call (three small kernels, no host
  * read-back); a caller that runs many layers / epochs on one graph builds it once with maxk_plan_build and
  * calls maxk_spgemm_forward_planned:
- *   plan       maxk_plan_bytes(n_rows) bytes, 16-byte aligned; a pure function of (row_begin, row_end, device)
+ *   plan       maxk_plan_bytes(n_rows) bytes, 16-byte aligned; a pure function of (row_begin, row_end, device).
+ *              Its last 256 bytes are the scheduler tickets of the launches that use it (each launch takes the
+ *              next of 32 slots and leaves it zeroed), so the buffer must stay writable and on its device.
  *   workspace  maxk_plan_workspace_bytes(n_rows) bytes of scratch, free again when the build has run
  */
 int maxk_spgemm_forward(const int32_t *row_begin, const int32_t *row_end,

@@ -15,20 +15,21 @@
 
 namespace maxk {
 
-constexpr int kPlanBuckets = 128;
+constexpr int kPlanBuckets = 256;
 constexpr int kPlanTileRows = 1024;          // rows per warp tile
 constexpr int kPlanThreads = 256;
 constexpr int kPlanWarps = kPlanThreads / 32;
 
-// degree -> bucket key, ascending key == descending degree.  4 sub-buckets per octave (rows of one
-// bucket differ by < 25 % in length), exact for degrees < 8.  Boundaries at every power of two, so
-// kPlanLongDeg and kPlanTailDeg are bucket boundaries.
+// degree -> bucket key, ascending key == descending degree.  8 sub-buckets per octave (rows of one
+// bucket differ by < 12.5 % in length: the lockstep of a group wastes ~4 % on a log-normal degree
+// distribution), exact for degrees < 16.  Boundaries at every power of two, so kPlanLongDeg and
+// kPlanTailDeg are bucket boundaries.
 __host__ __device__ inline int plan_key(int deg)
 {
     if (deg <= 0) return kPlanBuckets - 1;
     int msb = 0;
     for (int d = deg; d > 1; d >>= 1) ++msb;
-    const int fb = msb < 2 ? deg : 4 * (msb - 1) + ((deg >> (msb - 2)) & 3);
+    const int fb = msb < 3 ? deg : 8 * (msb - 2) + ((deg >> (msb - 3)) & 7);
     return kPlanBuckets - 1 - fb;
 }
 
@@ -144,7 +145,7 @@ using namespace maxk;
 extern "C" size_t maxk_plan_bytes(int64_t n_rows)
 {
     if (n_rows < 0) n_rows = 0;
-    return sizeof(int) * ((size_t)kPlanHeaderInts + 3 * (size_t)plan_pad_rows(n_rows));
+    return sizeof(int) * ((size_t)kPlanHeaderInts + 3 * (size_t)plan_pad_rows(n_rows) + 2 * kPlanTicketSlots);
 }
 
 extern "C" size_t maxk_plan_workspace_bytes(int64_t n_rows)
@@ -157,7 +158,7 @@ extern "C" size_t maxk_plan_workspace_bytes(int64_t n_rows)
 // half a wave of rows: what the last-wave rule of the plan compares the number of light rows with
 int plan_tail_rows()
 {
-    return device_sm_count() * 24 * kSS / 2;
+    return device_sm_count() * 16 * kSS / 2;      // 2 CTAs x 8 warps per SM (spgemm_fwd.cu)
 }
 
 extern "C" int maxk_plan_build(const int32_t *row_begin, const int32_t *row_end, int64_t n_rows, void *plan,
@@ -175,6 +176,10 @@ extern "C" int maxk_plan_build(const int32_t *row_begin, const int32_t *row_end,
     const int64_t n_pad = plan_pad_rows(n_rows);
     int *p_row = header + kPlanHeaderInts, *p_beg = p_row + n_pad, *p_end = p_beg + n_pad;
     const int tiles = n_tiles > 0 ? n_tiles : 1;
+    {   // scheduler tickets of the launches that will use this plan
+        cudaError_t err = cudaMemsetAsync(p_end + n_pad, 0, sizeof(int) * 2 * kPlanTicketSlots, stream);
+        if (err != cudaSuccess) return status_from_cuda(err);
+    }
     if (n_tiles == 0) {
         cudaError_t err = cudaMemsetAsync(hist, 0, sizeof(int) * kPlanBuckets, stream);
         if (err != cudaSuccess) return status_from_cuda(err);

@@ -34,6 +34,8 @@ constexpr int kPlanMagic = 0x4d41584b;      // "MAXK"
 constexpr int kPlanHeaderInts = 16;
 constexpr int kPlanLongDeg = 4096;          // rows with at least this many edges run in shared mode
 constexpr int kPlanTailDeg = 128;           // final-wave rows at least this long run in shared mode
+constexpr int kPlanTicketSlots = 32;        // (next item, finished warps) pairs behind the plan arrays: the dynamic
+                                            // scheduler state of up to 32 launches in flight on one plan
 
 // Row plan (device memory, int32): header, then three arrays of n_pad ints (row id, first edge, last edge
 // + 1) in PLAN ORDER = rows sorted by degree bucket, longest first, stable inside a bucket.
@@ -44,9 +46,29 @@ constexpr int kPlanTailDeg = 128;           // final-wave rows at least this lon
 struct PlanView {
     int n_rows, nA, nB, nC, nD, posC, posD, n_items;
     const int *p_row, *p_beg, *p_end;
+    int *tickets;
 };
 
 __host__ __device__ inline int64_t plan_pad_rows(int64_t n_rows) { return (n_rows + 31) / 32 * 32 + 32; }
+
+// Work items are handed out in plan order (heaviest first) by one atomic ticket counter per launch; the last warp
+// to leave puts the counter pair back to zero, so a launch needs no memset and no workspace of its own.
+__device__ __forceinline__ int grab_item(int *ticket, int lane)
+{
+    int v = 0;
+    if (lane == 0) v = atomicAdd(ticket, 1);
+    return __shfl_sync(kFullMask, v, 0);
+}
+__device__ __forceinline__ void leave_scheduler(int *ticket, int lane, int total_warps)
+{
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(ticket + 1, 1) == total_warps - 1) {
+            ticket[0] = 0;
+            ticket[1] = 0;
+        }
+    }
+}
 
 __device__ __forceinline__ PlanView load_plan(const int *plan)
 {
@@ -63,6 +85,7 @@ __device__ __forceinline__ PlanView load_plan(const int *plan)
     v.p_row = plan + kPlanHeaderInts;
     v.p_beg = v.p_row + n_pad;
     v.p_end = v.p_beg + n_pad;
+    v.tickets = const_cast<int *>(v.p_end + n_pad);
     return v;
 }
 

@@ -11,9 +11,10 @@
 //     lane (k = 32): every 128-byte line of a neighbour's CBSR row is touched by exactly one instruction;
 //   * the degree normalisation the reference does in a separate PyTorch pass (maxk_spgemm_function.py:86)
 //     is fused into the epilogue;
-//   * work is statically dealt to a persistent grid in plan order (longest items first), so there is no
-//     scheduler state to reset between launches and no second "long row" kernel.
+//   * work items are handed to a persistent grid in plan order (longest first) by one atomic ticket counter that
+//     the last warp resets: no memset, no workspace, no second "long row" kernel.
 #include "slots.cuh"
+#include <atomic>
 
 namespace maxk {
 
@@ -59,7 +60,7 @@ template <int K, int MINB>
 __global__ void __launch_bounds__(kFsThreads, MINB)
 spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ idx, const float *__restrict__ val,
                         const float *__restrict__ cval, const uint8_t *__restrict__ csel, float *__restrict__ out,
-                        int n_edges, int dim, int k, const float *__restrict__ row_div)
+                        int n_edges, int dim, int k, const float *__restrict__ row_div, int ticket_slot)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -74,18 +75,23 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
     float *acc_q = acc + kSL * q;
     const uint64_t keep = policy_evict_last();        // CBSR rows are re-used ~degree times: keep them in L2
     const int total_warps = gridDim.x * kFsWarps;
-    int item = blockIdx.x * kFsWarps + warp;
-    if (item >= pv.n_items) return;
+    int *ticket = pv.tickets + 2 * ticket_slot;
+    int item = grab_item(ticket, lane);
+    if (item >= pv.n_items) {
+        leave_scheduler(ticket, lane, total_warps);
+        return;
+    }
 
     // software pipeline over the warp's items: descriptors two items ahead; the first CSR window of the next
     // item is fetched as soon as the last window of the current one has been parked (pc/pw are free then)
     Item it_cur = decode_item(pv, item);
     Desc d_cur = load_desc(pv, it_cur, lane);
-    bool has_nxt = item + total_warps < pv.n_items;
+    int item_nxt = grab_item(ticket, lane);
+    bool has_nxt = item_nxt < pv.n_items;
     Desc d_nxt = d_cur;
     int sh_nxt = 0;
     if (has_nxt) {
-        const Item it = decode_item(pv, item + total_warps);
+        const Item it = decode_item(pv, item_nxt);
         d_nxt = load_desc(pv, it, lane);
         sh_nxt = it.shared;
     }
@@ -96,11 +102,12 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
 
     for (;;) {
         const SlotView sv = make_slot_view(d_cur, it_cur.shared, lane);
-        const bool has_nxt2 = item + 2 * total_warps < pv.n_items;
+        const int item_nxt2 = has_nxt ? grab_item(ticket, lane) : pv.n_items;
+        const bool has_nxt2 = item_nxt2 < pv.n_items;
         Desc d_nxt2 = d_nxt;
         int sh_nxt2 = 0;
         if (has_nxt2) {
-            const Item it = decode_item(pv, item + 2 * total_warps);
+            const Item it = decode_item(pv, item_nxt2);
             d_nxt2 = load_desc(pv, it, lane);
             sh_nxt2 = it.shared;
         }
@@ -225,13 +232,20 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
         __syncwarp();
 
         if (!has_nxt) break;
-        item += total_warps;
         it_cur.shared = sh_nxt;
         d_cur = d_nxt;
         d_nxt = d_nxt2;
         sh_nxt = sh_nxt2;
         has_nxt = has_nxt2;
     }
+    leave_scheduler(ticket, lane, total_warps);
+}
+
+// scheduler ticket slot of the next launch (launches that overlap on one plan must not share a slot)
+static int next_ticket_slot()
+{
+    static std::atomic<unsigned> counter{0};
+    return (int)(counter.fetch_add(1) % kPlanTicketSlots);
 }
 
 template <int K, int MINB>
@@ -257,7 +271,7 @@ static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const flo
         cfg.configured = true;
     }
     spgemm_fwd_slots_kernel<K, MINB><<<cfg.sms * cfg.blocks_per_sm, kFsThreads, smem, stream>>>(plan, idx, val, cval, csel,
-                                                                                                out, n_edges, dim, k, row_div);
+                                                                                                out, n_edges, dim, k, row_div, next_ticket_slot());
     return cudaGetLastError();
 }
 

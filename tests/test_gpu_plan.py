@@ -36,7 +36,7 @@ def test_plan_is_a_stable_degree_sort_of_the_rows(n, e, kind):
         if d <= 0:
             return 0
         msb = int(d).bit_length() - 1
-        return d if msb < 2 else 4 * (msb - 1) + ((d >> (msb - 2)) & 3)
+        return d if msb < 3 else 8 * (msb - 2) + ((d >> (msb - 3)) & 7)
     b = np.array([bucket(int(d)) for d in deg[rows]])
     assert (np.diff(b) <= 0).all()                                       # longest buckets first
     same = np.diff(b) == 0
