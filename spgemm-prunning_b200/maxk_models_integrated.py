@@ -9,8 +9,8 @@ but one fused CUDA pass (exact top-k + masked row + CBSR emission) instead of
 topk + zeros_like + scatter_ + multiply, and the state kept for backward is the uint8 selector
 [N, k] instead of an fp32 [N, 256] mask.
 
-The conv layers / models of the reference file are callers of this path and
-are not part of this package.
+The conv layers / models of the reference (model_integrated_v3.py:62-752) follow below, on raw CSR tensors
+instead of a DGL graph.
 """
 import torch
 from torch.autograd import Function
@@ -46,9 +46,13 @@ class MaxK(Function):
 class OPTMaxK(Function):
     """MaxK activation that also returns the CBSR pair (model_integrated_v3.py:28-43).
 
-    topk_indices is int64 like torch.topk's (it may be fed to scatter_/gather by callers); the
-    entries of a row are in bank-residue-major column order, not value order -- every consumer on this path
-    (spmm, scatter) is order-independent.
+    topk_indices is int64 like torch.topk's (it may be fed to scatter_/gather by callers).  Entry order inside a
+    row: `OPTMaxK.order = "banked"` (default, the order the SpGEMM kernel is fastest on; every consumer on this
+    path -- spmm, scatter -- is order-independent) or `"value_desc"`, torch.topk's own order (values descending,
+    lowest column first on ties), i.e. exactly what the reference class returns.
+
+    In-tree callers pass uint8_indices=True and get the kernel's uint8 selectors instead of an int64 copy (the
+    aggregation operator needs uint8; the int64 round trip costs N*k*9 bytes of traffic per layer).
 
     reference_compat: the reference's backward returns grad_output * mask only and DROPS
     grad_topk_values (model_integrated_v3.py:40-43), so the aggregation branch
@@ -57,14 +61,19 @@ class OPTMaxK(Function):
     reproduce the reference bit for bit.
     """
     reference_compat = False
+    order = "banked"
 
     @staticmethod
-    def forward(ctx, input, k=1):
+    def forward(ctx, input, k=1, uint8_indices=False):
         _require_cuda_2d(input, "OPTMaxK")
-        r = _k.topk_cbsr(input, int(k), order=_k.ORDER_BANKED, want_masked=True, want_i64=True)
+        if OPTMaxK.order not in ("banked", "value_desc"):
+            raise ValueError('OPTMaxK.order must be "banked" or "value_desc"')
+        order = _k.ORDER_BANKED if OPTMaxK.order == "banked" else _k.ORDER_VALUE_DESC
+        r = _k.topk_cbsr(input, int(k), order=order, want_masked=True, want_i64=not uint8_indices)
         ctx.save_for_backward(r["sel"])
-        ctx.mark_non_differentiable(r["i64"])
-        return r["masked"], r["values"], r["i64"]
+        idx = r["sel"] if uint8_indices else r["i64"]
+        ctx.mark_non_differentiable(idx)
+        return r["masked"], r["values"], idx
 
     @staticmethod
     def backward(ctx, grad_output, grad_topk_values, grad_topk_indices):
@@ -72,7 +81,7 @@ class OPTMaxK(Function):
         add = None
         if grad_topk_values is not None and not OPTMaxK.reference_compat:
             add = grad_topk_values.contiguous()
-        return _k.mask_apply(grad_output.contiguous(), sel, add), None
+        return _k.mask_apply(grad_output.contiguous(), sel, add), None, None
 
 
 
@@ -163,11 +172,10 @@ class MaxKSAGEConv(nn.Module):
     def forward(self, graph, feat, topk_values=None, topk_indices=None):
         if topk_values is None or topk_indices is None:
             raise RuntimeError("topk_values / topk_indices REQUIRED")               # :149-150
-        if self._in_src_feats > self._out_feats:
-            # the reference applies fc_neigh to the [N, k] top-k values here (:165), which only type-checks
-            # when k == in_feats; there is no k-sparse operand left to aggregate after a dense Linear.
-            raise NotImplementedError("in_feats > out_feats: the reference's transform-before-aggregate branch "
-                                      "is shape-inconsistent for k != in_feats")
+        # in_feats > out_feats: the reference switches to transform-before-aggregate here (:161-172), but applies
+        # fc_neigh to the [N, k] top-k VALUES, which only type-checks when k == in_feats == out_feats.  The order is
+        # a FLOP optimisation, not a different function -- A (X_s W) == (A X_s) W -- and only the k-sparse X_s can go
+        # through the CBSR kernels, so both cases aggregate first and transform afterwards.
         h_self = self.feat_drop(feat)
         h_neigh = self.fc_neigh(graph.aggregate(topk_values, topk_indices))           # :175-182
         rst = self.fc_self(h_self) + h_neigh                                          # :185
@@ -207,9 +215,7 @@ class MaxKGraphConv(nn.Module):
             raise ValueError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid.")  # :281-290
         rst = graph.aggregate(topk_values, topk_indices)                              # :341-346 (aggregate then transform)
         if self.weight is not None:
-            if self._in_feats > self._out_feats:
-                raise NotImplementedError("in_feats > out_feats: see MaxKSAGEConv")
-            rst = torch.matmul(rst, self.weight)                                       # :348-349
+            rst = torch.matmul(rst, self.weight)                                       # :327-349; A (X_s W) == (A X_s) W, see MaxKSAGEConv
         if self._norm in ("right", "both"):                                           # :378-386
             degs = graph.in_degrees().to(rst).clamp(min=1)
             rst = rst * (torch.pow(degs, -0.5) if self._norm == "both" else 1.0 / degs).unsqueeze(-1)
@@ -265,7 +271,7 @@ class MaxKSAGE(nn.Module):
     def forward(self, g, x):
         x = self.lin_in(x)
         for layer in self.layers:
-            x_sparse, topk_values, topk_indices = OPTMaxK.apply(x, self.k_value)      # :581
+            x_sparse, topk_values, topk_indices = OPTMaxK.apply(x, self.k_value, True)      # :581
             x = layer(g, x_sparse, topk_values, topk_indices)
         return self.lin_out(x)
 
@@ -295,7 +301,7 @@ class _MaxKStack(nn.Module):
         x = self.lin_in(x).relu()
         for i in range(self.num_layers):
             x = self.linlayers[i](x)
-            x_sparse, topk_values, topk_indices = OPTMaxK.apply(x, self.k_value)
+            x_sparse, topk_values, topk_indices = OPTMaxK.apply(x, self.k_value, True)
             x_sparse = self.dropoutlayers[i](x_sparse)
             x = self.convlayers[i](g, x_sparse, topk_values, topk_indices)
             if self.norm_flag:

@@ -1,49 +1,38 @@
-"""MaxK SpGEMM autograd operator, generation 1 surface.
+"""MaxK SpGEMM autograd operator, generation 2 surface (reference maxk_spgemm_function_v2.py:20-267).
 
-Same names, argument order and return arity as the reference's maxk_spgemm_function.py
-(MaxKSpGEMMFunction :20-186, maxk_spgemm :188-212, MaxKSpmmWrapper :214-267), running on the
-hand-written sm_100a kernels of this package:
+Same names, argument order and return arity as generation 1 (maxk_spgemm_function.py in this package).
+The one behavioural difference of the reference's v2 is kept: its backward multiplies the incoming
+gradient by the top-k mask of the INPUT before the degree normalisation
+(maxk_spgemm_function_v2.py:149-150, `grad_output = grad_output * mask`).  That is not part of the
+adjoint of the forward, so it can be switched off (`MaxKSpGEMMFunction.mask_grad_output = False` gives
+generation 1's exact adjoint); it is on by default because it is what this generation computes.  The mask
+is rebuilt from the uint8 selectors (maxk_mask_apply) instead of a saved [N, 256] fp32 tensor (:56-58, :73).
 
-    forward : top-k -> CBSR (one fused kernel), SpGEMM with the /in_degrees fused in the epilogue
-    backward: SSpMM with the /out_degrees fused in the row stage, scatter to dense [N, 256]
-
-Backward and the CSC arrays: like the reference (:164-172) the backward walks the row ranges of the CSR
-(row_begin / row_end of A, recovered from the CSR warp4 quads or graph_indptr) over graph_indices_T /
-graph_values_T when they are given.  The kernel computes gs[c] += val[e] * g[r] for edge e = (r, c) of WHATEVER
-arrays it is handed, so this is the adjoint of the forward only when A's pattern and edge values are symmetric
-and the CSC arrays list every row's neighbours in the same positions as the CSR (the reference's own assumption:
-undirected graphs with unit weights).  For a directed graph or asymmetric edge values pass no *_T arrays -- the
-CSR arrays are then used, which is the exact adjoint for any graph -- or use spgemmfunction_v3, which takes the
-CSC quads.  When the edge counts differ the mismatch is detectable and raises.
-
-Deliberate differences: the reference's arity bug (3 tensors saved, 7
-unpacked, :66 vs :144; 7 Nones returned for 11 inputs, :184) is fixed; nothing is printed; there
-is no cuSPARSE / torch.sparse fallback -- a failure raises.
+The reference's arity bug (4 tensors saved :73, 5 unpacked :146; 7 Nones returned for 11 inputs :185) is
+fixed, nothing is printed, and there is no cuSPARSE / torch.sparse fallback (:94-131): a failure raises.
 """
 import torch
 from torch.autograd import Function
 
 import maxk_cuda_kernels
+from maxk_spgemm_function import _row_ranges
 
 MAXK_KERNELS_AVAILABLE = True   # importing maxk_cuda_kernels raises if the library is missing
 
 
-def _row_ranges(warp4_metadata, num_warps, graph_indptr, n_rows):
-    """(row_begin, row_end, row plan) from the CSR indptr when given, else from the warp4 quads."""
-    return maxk_cuda_kernels.rows_and_plan(warp4_metadata, num_warps, graph_indptr, n_rows)
-
-
 class MaxKSpGEMMFunction(Function):
+    mask_grad_output = True
+
     @staticmethod
     def forward(ctx, graph_indices, graph_values, input_features, k_value,
                 warp4_metadata, num_warps, graph_indptr=None, in_degrees=None, out_degrees=None,
                 graph_indices_T=None, graph_values_T=None):
         n, d = input_features.shape
         k_value = int(k_value)
-        if k_value < d:                                        # maxk_spgemm_function.py:51-57
+        if k_value < d:                                                        # :51-57
             r = maxk_cuda_kernels.topk_cbsr(input_features, k_value, order=maxk_cuda_kernels.ORDER_BANKED)
             sparse_data, sparse_selector = r["values"], r["sel"]
-        else:                                                  # :58-63, k >= D keeps every feature
+        else:                                                                  # :58-64, k >= D keeps every feature
             if d > maxk_cuda_kernels.FULL_DIM:
                 raise RuntimeError("feature dim %d > 256 cannot be addressed by uint8 selectors" % d)
             sparse_data = input_features.contiguous()
@@ -52,23 +41,25 @@ class MaxKSpGEMMFunction(Function):
         bwd_indices = graph_indices_T if graph_indices_T is not None else graph_indices
         bwd_values = graph_values_T if graph_values_T is not None else graph_values
         if bwd_indices.numel() != graph_indices.numel() or bwd_values.numel() != graph_indices.numel():
-            raise RuntimeError("graph_indices_T / graph_values_T must hold the same number of edges as the CSR arrays: "
-                               "the backward walks the CSR row ranges over them (see the module docstring)")
+            raise RuntimeError("graph_indices_T / graph_values_T must hold the same number of edges as the CSR arrays")
         saved_deg = out_degrees if out_degrees is not None else torch.empty(0, device=input_features.device)
         ctx.save_for_backward(bwd_indices, bwd_values, sparse_selector, row_begin, row_end, saved_deg)
         ctx.has_out_degrees = out_degrees is not None
         ctx.input_shape = (n, d)
         return maxk_cuda_kernels.spgemm_forward_csr(
             row_begin, row_end, graph_indices, graph_values, sparse_data, sparse_selector,
-            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=in_degrees, plan=plan)          # :76-86
+            out_dim=maxk_cuda_kernels.FULL_DIM, row_div=in_degrees, plan=plan)  # :76-92
 
     @staticmethod
     def backward(ctx, grad_output):
         bwd_indices, bwd_values, sparse_selector, row_begin, row_end, out_degrees = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        if MaxKSpGEMMFunction.mask_grad_output and grad_output.size(1) == ctx.input_shape[1]:   # :149-150
+            grad_output = maxk_cuda_kernels.mask_apply(grad_output, sparse_selector)
         grad_sparse = maxk_cuda_kernels.sspmm_backward_csr(
-            row_begin, row_end, bwd_indices, bwd_values, grad_output.contiguous(), sparse_selector,
-            row_div=out_degrees if ctx.has_out_degrees else None)            # :155-172
-        grad_input = maxk_cuda_kernels.cbsr_scatter(grad_sparse, sparse_selector, dim=ctx.input_shape[1])  # :152,175
+            row_begin, row_end, bwd_indices, bwd_values, grad_output, sparse_selector,
+            row_div=out_degrees if ctx.has_out_degrees else None)                # :154-172
+        grad_input = maxk_cuda_kernels.cbsr_scatter(grad_sparse, sparse_selector, dim=ctx.input_shape[1])  # :152,176
         return None, None, grad_input, None, None, None, None, None, None, None, None
 
 
@@ -81,7 +72,7 @@ def maxk_spgemm(graph_indices, graph_values, input_features, k_value,
 
 
 class MaxKSpmmWrapper:
-    """Holds the warp4 metadata of one graph (maxk_spgemm_function.py:214-267)."""
+    """Holds the warp4 metadata of one graph (maxk_spgemm_function_v2.py:215-268)."""
 
     def __init__(self, graph_name="", num_warps=12, warp_max_nz=64):
         self.graph_name = graph_name
@@ -91,7 +82,6 @@ class MaxKSpmmWrapper:
         self.warp_max_nz = warp_max_nz
 
     def load_metadata(self, graph_name=None):
-        """Reads kernels/w12_nz64_warp_4/<graph>.warp4 like the reference; raises if it is missing."""
         if graph_name is None:
             graph_name = self.graph_name
         self.warp4_metadata = maxk_cuda_kernels.load_warp4_metadata(graph_name, self.num_warps_config, self.warp_max_nz)
@@ -99,7 +89,7 @@ class MaxKSpmmWrapper:
         return True
 
     def build_metadata(self, graph_indptr):
-        """Additive: builds the same quads on the GPU from the CSR indptr (no file, no host loop)."""
+        """Additive: the same quads built on the GPU from the CSR indptr (no file, no host loop)."""
         self.warp4_metadata, self.num_warps = maxk_cuda_kernels.build_warp4(graph_indptr, self.warp_max_nz)
         return True
 

@@ -17,7 +17,10 @@ def pytest_configure(config):
     # without a GPU; this is a build step, not a fallback -- the product still raises if the .so is missing)
     import _build
     if _build.needs_build():
-        _build.build()
+        try:
+            _build.build()
+        except Exception as ex:   # no nvcc on this machine: the pure-CPU tests (oracle, host logic) still run;
+            config._maxk_build_error = repr(ex)    # tests that load the library fail with the ImportError it raises
 
 
 def pytest_collection_modifyitems(config, items):

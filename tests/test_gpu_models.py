@@ -95,3 +95,67 @@ def test_layers_validate_inputs():
     with pytest.raises(ValueError):
         MaxKSAGEConv(256, 256, aggregator_type="pool")
     assert isinstance(MaxKSAGEConv(256, 256, norm=nn.LayerNorm(256)).norm, nn.LayerNorm)
+
+
+def test_conv_layers_with_more_inputs_than_outputs():
+    """in_feats > out_feats (the reference's transform-before-aggregate case, model_integrated_v3.py:161-172,
+    327-339): A (X_s W) == (A X_s) W, so the layers aggregate the k-sparse features and transform afterwards."""
+    from maxk_models_integrated import MaxKGraphConv, MaxKSAGEConv, OPTMaxK
+    torch.manual_seed(1)
+    gc, a = _graph()
+    n, k = gc.num_nodes(), 16
+    h = torch.randn(n, 256, device="cuda")
+    hs, tv, ti = OPTMaxK.apply(h, k, True)
+    agg = _ref_aggregate(a, gc.degrees, h, k)
+    sage = MaxKSAGEConv(256, 64, k_value=k).cuda()
+    torch.testing.assert_close(sage(gc, hs, tv, ti), sage.fc_self(hs) + sage.fc_neigh(agg), rtol=1e-4, atol=1e-5)
+    gcn = MaxKGraphConv(256, 64, norm="both", k_value=k, allow_zero_in_degree=True).cuda()
+    exp = torch.matmul(agg, gcn.weight) * torch.pow(gc.degrees, -0.5).unsqueeze(-1) + gcn.bias
+    torch.testing.assert_close(gcn(gc, hs, tv, ti), exp, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("module", ["maxk_spgemm_function_v2", "spgemmfunction_v2"])
+def test_v2_operator_generations(module):
+    """Generation-2 surfaces (reference maxk_spgemm_function_v2.py, spgemmfunction_v2): same call shapes as their
+    generation-1 / "optimized" siblings; v2 of the feature-input operator masks the incoming gradient with the
+    input's top-k mask (maxk_spgemm_function_v2.py:149-150)."""
+    import importlib
+    import numpy as np
+    import oracle
+    from synth_graphs import synth_graph
+    mod = importlib.import_module(module)
+    g = synth_graph(500, 6000, seed=4)
+    ip, ix, va = g["indptr"].cuda(), g["indices"].cuda(), g["values"].cuda()
+    deg = torch.clamp((ip[1:] - ip[:-1]).float(), min=1)
+    k = 32
+    x = torch.randn(500, 256, device="cuda", requires_grad=True)
+    up = torch.rand(500, 256, device="cuda")
+    w = mod.MaxKSpmmWrapper("toy")
+    w.build_metadata(ip)
+    vals, cols = oracle.topk(x.detach().cpu().numpy(), k, 2)
+    sel = cols.astype(np.uint8)
+    ipn, ixn, van, dn = ip.cpu().numpy(), ix.cpu().numpy(), va.cpu().numpy(), deg.cpu().numpy()
+    exp_out = oracle.spgemm_fwd(ipn, ixn, van, vals, sel, deg=dn)
+    if module == "maxk_spgemm_function_v2":
+        out = w.spmm(ix, va, x, k, graph_indptr=ip, in_degrees=deg, out_degrees=deg)
+        out.backward(up)
+        torch.testing.assert_close(out.detach().cpu(), torch.from_numpy(exp_out), rtol=1e-5, atol=1e-6)
+        mask = oracle.scatter_dense(np.ones_like(vals), cols)
+        gs = oracle.sspmm_bwd(ipn, ixn, van, up.cpu().numpy() * mask, sel, deg=dn)
+        torch.testing.assert_close(x.grad.cpu(), torch.from_numpy(oracle.scatter_dense(gs, cols)), rtol=2e-5, atol=1e-6)
+        mod.MaxKSpGEMMFunction.mask_grad_output = False
+        try:
+            x.grad = None
+            w.spmm(ix, va, x, k, graph_indptr=ip, in_degrees=deg, out_degrees=deg).backward(up)
+        finally:
+            mod.MaxKSpGEMMFunction.mask_grad_output = True
+        gs = oracle.sspmm_bwd(ipn, ixn, van, up.cpu().numpy(), sel, deg=dn)
+        torch.testing.assert_close(x.grad.cpu(), torch.from_numpy(oracle.scatter_dense(gs, cols)), rtol=2e-5, atol=1e-6)
+    else:
+        tv = torch.from_numpy(vals).cuda().requires_grad_(True)
+        ti = torch.from_numpy(cols.astype(np.int64)).cuda()
+        out = w.spmm(ix, va, tv, ti, ip, deg, deg, ix, va)
+        out.backward(up)
+        torch.testing.assert_close(out.detach().cpu(), torch.from_numpy(exp_out), rtol=1e-5, atol=1e-6)
+        gs = oracle.sspmm_bwd(ipn, ixn, van, up.cpu().numpy(), sel, deg=dn)
+        torch.testing.assert_close(tv.grad.cpu(), torch.from_numpy(gs), rtol=2e-5, atol=1e-6)

@@ -75,6 +75,25 @@ def test_maxk_and_optmaxk_match_reference_classes(ref_py, k):
     assert_close(gf, full, "OPTMaxK backward incl. grad_topk_values")
 
 
+@pytest.mark.parametrize("k", [8, 32])
+def test_optmaxk_value_desc_order_is_the_reference_output(ref_py, k):
+    """OPTMaxK.order = "value_desc": (topk_values, topk_indices) are torch.topk's, element for element, as the
+    reference class returns them (model_integrated_v3.py:32); uint8_indices=True hands out the kernel's selectors."""
+    from maxk_models_integrated import OPTMaxK
+    x = _t(ref_py["maxk_x"])
+    OPTMaxK.order = "value_desc"
+    try:
+        yo, tv, ti = OPTMaxK.apply(x, k)
+        _, tv8, ti8 = OPTMaxK.apply(x, k, True)
+    finally:
+        OPTMaxK.order = "banked"
+    assert ti.dtype == torch.int64 and ti8.dtype == torch.uint8
+    assert np.array_equal(tv.cpu().numpy(), ref_py["optmaxk_vals_k%d" % k])
+    assert np.array_equal(ti.cpu().numpy(), ref_py["optmaxk_idx_k%d" % k])
+    assert np.array_equal(ti8.cpu().numpy().astype(np.int64), ref_py["optmaxk_idx_k%d" % k]) and torch.equal(tv8, tv)
+    assert np.array_equal(yo.cpu().numpy(), ref_py["optmaxk_fwd_k%d" % k])
+
+
 # ------------------------------------------------------------------- golden: reference CUDA kernels
 @pytest.mark.parametrize("name", ["k32", "k64"])
 def test_entry_points_match_reference_cuda_kernels(ref_cuda, name):
