@@ -80,7 +80,9 @@ template <> struct SelLoad<2> {
 // Fast path, k in {8, 16, 32, 64}: a lane owns EPL consecutive entries of one destination row,
 // L = k/EPL lanes cover an edge, EPI = 32/L edges per warp instruction; one vector reduction
 // (16 B, or 8 B for k = 8) per lane per edge.
-template <int K, int UNROLL, bool PREFETCHED>
+// KS = entries per CBSR row.  KS == K for k in {8, 16, 32, 64}; k = 96 / 128 run the k = 32 lane layout over
+// KS / 32 chunks of every row (each chunk is one full 128-byte line of gs, one vector reduction per lane).
+template <int K, int KS, int UNROLL, bool PREFETCHED>
 __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const float *__restrict__ val,
                                              const uint8_t *__restrict__ csel, float *__restrict__ gs,
                                              const float *gsm, int b, int e, int batch0, int stride, int first_c,
@@ -115,6 +117,7 @@ __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const 
             nxt_c = ld_stream_i32(idx + nb + lane);
             nxt_w = ld_stream_f32(val + nb + lane);
         }
+        for (int ch = 0; ch < KS / K; ++ch)
         for (int j = 0; j < n; j += EPI * UNROLL) {
             uint32_t s[UNROLL];
             float w[UNROLL];
@@ -126,7 +129,7 @@ __device__ __forceinline__ void scatter_fast(const int *__restrict__ idx, const 
                 const int c = __shfl_sync(kFullB, my_c, ej & 31);
                 w[u] = __shfl_sync(kFullB, my_w, ej & 31);
                 ok[u] = ej < n;
-                off[u] = (size_t)c * K + EPL * t;
+                off[u] = (size_t)c * KS + ch * K + EPL * t;
                 s[u] = 0;
                 if (ok[u]) s[u] = SelLoad<EPL>::load(csel + off[u], keep);
             }
@@ -168,13 +171,19 @@ __device__ __forceinline__ void scatter_any_k(const int *__restrict__ idx, const
     }
 }
 
+// lane layout used for a row width: k = 96 / 128 borrow the k = 32 layout (3 / 4 chunks per row)
+template <int K> struct BwdLay {
+    static constexpr int LK = (K == 96 || K == 128) ? 32 : K;
+    using LY = Lay<LK>;
+};
+
 template <int K, bool PREFETCHED>
 __device__ __forceinline__ void scatter_row(const int *idx, const float *val, const uint8_t *csel, float *gs,
                                             const float *gsm, int k, int b, int e, int batch0, int stride,
                                             int first_c, float first_w)
 {
-    if constexpr (Lay<K>::kFast)
-        scatter_fast<K, 4, PREFETCHED>(idx, val, csel, gs, gsm, b, e, batch0, stride, first_c, first_w);
+    if constexpr (BwdLay<K>::LY::kFast)
+        scatter_fast<BwdLay<K>::LK, K, 4, PREFETCHED>(idx, val, csel, gs, gsm, b, e, batch0, stride, first_c, first_w);
     else scatter_any_k(idx, val, csel, gs, gsm, k, b, e, batch0, stride);
 }
 
@@ -188,7 +197,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = lane_id();
-    float *gsm = smem + (threadIdx.x >> 5) * Lay<K>::kWords;
+    float *gsm = smem + (threadIdx.x >> 5) * BwdLay<K>::LY::kWords;
     for (;;) {
         int first = 0;
         if (lane == 0) first = atomicAdd(&ws->row_counter, rows_per_grab);
@@ -208,7 +217,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
         float pg[kAccDim / 32];
         if (ne > nb && ne - nb <= kLongRow) {
             load_g_row(g + (size_t)first * dim, dim, pg);
-            if (Lay<K>::kFast && nb + lane < ne) {
+            if (BwdLay<K>::LY::kFast && nb + lane < ne) {
                 pc = ld_stream_i32(idx + nb + lane);
                 pw = ld_stream_f32(val + nb + lane);
             }
@@ -228,7 +237,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
                 pw = 0.f;
                 if (ne > nb && ne - nb <= kLongRow) {
                     load_g_row(g + (size_t)(r + 1) * dim, dim, pg);
-                    if (Lay<K>::kFast && nb + lane < ne) {
+                    if (BwdLay<K>::LY::kFast && nb + lane < ne) {
                         pc = ld_stream_i32(idx + nb + lane);
                         pw = ld_stream_f32(val + nb + lane);
                     }
@@ -241,7 +250,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
             }
             const bool has_div = row_div != nullptr;
             __syncwarp();
-            stage_row<K>(cg, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
+            stage_row<BwdLay<K>::LK>(cg, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
             scatter_row<K, true>(idx, val, csel, gs, gsm, k, b, e, 0, 1, cur_c, cur_w);
         }
     }
@@ -257,7 +266,7 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_item;
     const int warp = threadIdx.x >> 5;
-    float *gsm = smem + warp * Lay<K>::kWords;
+    float *gsm = smem + warp * BwdLay<K>::LY::kWords;
     const int n_long = ws->long_count;
     for (;;) {
         __syncthreads();
@@ -270,7 +279,7 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
         const bool has_div = row_div != nullptr;
         float gv[kAccDim / 32];
         load_g_row(g + (size_t)r * dim, dim, gv);
-        stage_row<K>(gv, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
+        stage_row<BwdLay<K>::LK>(gv, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
         scatter_row<K, false>(idx, val, csel, gs, gsm, k, b, e, warp, kBwdLongWarps, 0, 0.f);
     }
 }
@@ -292,8 +301,8 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
                               int64_t n_edges, int dim, int k, const float *row_div, SchedWorkspace *ws,
                               bool zero_fill, cudaStream_t stream)
 {
-    const size_t smem_main = (size_t)kBwdWarps * Lay<K>::kWords * sizeof(float);
-    const size_t smem_long = (size_t)kBwdLongWarps * Lay<K>::kWords * sizeof(float);
+    const size_t smem_main = (size_t)kBwdWarps * BwdLay<K>::LY::kWords * sizeof(float);
+    const size_t smem_long = (size_t)kBwdLongWarps * BwdLay<K>::LY::kWords * sizeof(float);
     static LaunchConfig cache[kMaxCachedDevices];  // per template instance and device
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
@@ -353,6 +362,8 @@ static int sspmm_backward_impl(bool zero_fill, const int32_t *row_begin, const i
         case 16: err = launch_bwd<16>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
         case 32: err = launch_bwd<32>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
         case 64: err = launch_bwd<64>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        case 96: err = launch_bwd<96>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        case 128: err = launch_bwd<128>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
         default: err = launch_bwd<0>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
     }
     return status_from_cuda(err);

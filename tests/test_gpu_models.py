@@ -159,3 +159,36 @@ def test_v2_operator_generations(module):
         torch.testing.assert_close(out.detach().cpu(), torch.from_numpy(exp_out), rtol=1e-5, atol=1e-6)
         gs = oracle.sspmm_bwd(ipn, ixn, van, up.cpu().numpy(), sel, deg=dn)
         torch.testing.assert_close(tv.grad.cpu(), torch.from_numpy(gs), rtol=2e-5, atol=1e-6)
+
+
+def test_training_step_gradients_at_the_yelp_shape():
+    """BASELINE.json config 3 (Yelp-shape GCN, MaxK k = 32, hidden 256, 3 layers): loss and every parameter gradient
+    of ONE full-graph training step against the torch restatement (torch.topk + scatter + torch.sparse mm) at the
+    full graph size (716,847 nodes, ~14 M edges)."""
+    from maxk_gnn_training import synthetic_task
+    from maxk_models_integrated import MaxKGCN
+    torch.manual_seed(0)
+    gc, x, y, masks = synthetic_task("yelp", 1.0, 128, 16, torch.device("cuda"))
+    n, k = gc.num_nodes(), 32
+    model = MaxKGCN(128, 256, 3, 16, maxk=k, feat_drop=0.0, norm=True, graph_name="yelp").cuda()
+    lossf = torch.nn.functional.binary_cross_entropy_with_logits
+    out = model(gc, x)
+    loss = lossf(out[masks[0]], y[masks[0]])
+    loss.backward()
+    grads = {name: p.grad.clone() for name, p in model.named_parameters() if p.grad is not None}
+    a = torch.sparse_csr_tensor(gc.indptr.long(), gc.indices.long(), gc.values, size=(n, n))
+    deg = gc.degrees
+    model.zero_grad()
+    h = model.lin_in(x).relu()
+    for i in range(model.num_layers):
+        h = model.linlayers[i](h)
+        agg = _ref_aggregate(a, deg, h, k)
+        h = model.normlayers[i](agg * torch.pow(deg, -0.5).unsqueeze(-1))
+    ref = model.lin_out(h)
+    ref_loss = lossf(ref[masks[0]], y[masks[0]])
+    ref_loss.backward()
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-4)
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            torch.testing.assert_close(grads[name], p.grad, rtol=5e-3, atol=1e-6, msg=lambda m, n=name: n + ": " + m)

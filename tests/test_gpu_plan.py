@@ -80,3 +80,21 @@ def test_plan_of_another_graph_is_rejected():
     with pytest.raises(RuntimeError):
         kern.spgemm_forward_csr(ip[:-2], ip[1:-1], g["indices"].cuda(), g["values"].cuda(), torch.zeros(100, 32).cuda(),
                                 torch.zeros(100, 32, dtype=torch.uint8).cuda(), plan=plan)
+
+
+@pytest.mark.parametrize("k", [96, 128])
+@pytest.mark.parametrize("n,e,kind", [(997, 30000, "powerlaw"), (64, 64 * 4500, "uniform")])
+def test_backward_wide_rows_match_the_oracle(k, n, e, kind):
+    """k = 96 / 128: the backward runs the k = 32 lane layout over 3 / 4 chunks of every CBSR row."""
+    import maxk_cuda_kernels as kern
+    g = synth_graph(n, e, seed=k, kind=kind)
+    ip, ix, va = g["indptr"].cuda(), g["indices"].cuda(), g["values"].cuda()
+    gen = torch.Generator().manual_seed(k)
+    x, grad = torch.randn(n, 256, generator=gen), torch.rand(n, 256, generator=gen)
+    _, cols = oracle.topk(x.numpy(), k, 2)
+    sel = cols.astype(np.uint8)
+    deg = np.maximum(np.diff(g["indptr"].numpy()), 1).astype(np.float32)
+    gs = kern.sspmm_backward_csr(ip[:-1], ip[1:], ix, va, grad.cuda(), torch.from_numpy(sel).cuda(),
+                                 row_div=torch.from_numpy(deg).cuda())
+    exp = oracle.sspmm_bwd(g["indptr"].numpy(), g["indices"].numpy(), g["values"].numpy(), grad.numpy(), sel, deg=deg)
+    assert_close(gs, exp, "backward k=%d" % k, rtol=2e-5)
