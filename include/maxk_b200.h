@@ -191,6 +191,29 @@ int maxk_warp4_to_rows(const int32_t *warp4, int64_t n_quads, int64_t n_rows,
                        int32_t *row_begin, int32_t *row_end, maxk_stream_t stream);
 
 /*
+ * (6) Feature widths above 256: CBSR with uint16 column selectors, dim <= 1024.
+ * The reference cannot address them: it casts torch.topk's indices to uint8 (maxk_spgemm_function.py:57) and
+ * hard-wires 256 output columns (cuda_kernel_bindings.cpp:70), although its own Yelp script trains with hidden 384
+ * (scripts_train/yelp_maxk.sh:16).  Same contracts as (1)-(3) with
+ *   cbsr_sel  [n, k] uint16, entries in column-ascending order, k <= 256
+ *   out / g   [n_rows, dim] fp32 dense rows of dim <= 1024 floats (out 32-byte aligned, dim % 8 == 0 for the vector stores)
+ * The forward runs on a row plan (maxk_plan_build); both operators need
+ * maxk_wide_workspace_bytes(n_rows, n_src, dim, k) bytes of 256-byte aligned scratch (n_src = rows of the CBSR).
+ */
+int maxk_topk_cbsr16(const float *x, int64_t n_rows, int dim, int k,
+                     float *cbsr_val, uint16_t *cbsr_sel, float *masked, maxk_stream_t stream);
+size_t maxk_wide_workspace_bytes(int64_t n_rows, int64_t n_src, int dim, int k);
+int maxk_spgemm_forward16(const void *plan, const int32_t *indices, const float *values,
+                          const float *cbsr_val, const uint16_t *cbsr_sel,
+                          float *out, int64_t n_rows, int64_t n_src, int64_t n_edges, int dim, int k,
+                          const float *row_div, void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+int maxk_sspmm_backward16(const int32_t *row_begin, const int32_t *row_end,
+                          const int32_t *indices, const float *values,
+                          const float *g, const uint16_t *cbsr_sel,
+                          float *gs, int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
+                          const float *row_div, void *workspace, size_t workspace_bytes, maxk_stream_t stream);
+
+/*
  * (5) Helpers of the operator surface.
  * maxk_cbsr_scatter: dense[r, sel[r,l]] = vals[r,l], everything else 0.  Replaces
  *   zeros(...).scatter_(1, sel.long(), grad_sparse) (maxk_spgemm_function.py:152,175).

@@ -146,9 +146,16 @@ int64_t oracle_warp4(const int32_t *indptr, int64_t N, int max_nz, int32_t *out)
  * deg (nullable): fp32 divisor applied AFTER the sum exactly as the Python layer does
  *   (maxk_spgemm_function.py:86, spgemmfunction_v4:72): out32 = float(sum); out32 /= deg[r].
  */
-void oracle_spgemm_fwd(const int32_t *indptr, const int32_t *idx, const float *val,
-                       const float *data, const uint8_t *sel,
-                       int64_t n_rows, int k, int D, const float *deg, float *out)
+/* selector width: the reference's format is uint8 (kernels/spmm_maxk.cu:17); the wide path (dim > 256)
+ * stores uint16 -- same loops, wider index */
+static inline int sel_get(const void *sel, int wide, int64_t i)
+{
+    return wide ? (int)((const uint16_t *)sel)[i] : (int)((const uint8_t *)sel)[i];
+}
+
+static void spgemm_fwd_impl(const int32_t *indptr, const int32_t *idx, const float *val,
+                            const float *data, const void *sel, int wide,
+                            int64_t n_rows, int k, int D, const float *deg, float *out)
 {
 #pragma omp parallel
     {
@@ -160,8 +167,7 @@ void oracle_spgemm_fwd(const int32_t *indptr, const int32_t *idx, const float *v
                 int64_t c = idx[e];
                 double w = (double)val[e];
                 const float *dv = data + c * k;
-                const uint8_t *sv = sel + c * k;
-                for (int l = 0; l < k; ++l) acc[sv[l]] += w * (double)dv[l];
+                for (int l = 0; l < k; ++l) acc[sel_get(sel, wide, c * k + l)] += w * (double)dv[l];
             }
             for (int j = 0; j < D; ++j) {
                 float o = (float)acc[j];
@@ -171,6 +177,20 @@ void oracle_spgemm_fwd(const int32_t *indptr, const int32_t *idx, const float *v
         }
         free(acc);
     }
+}
+
+void oracle_spgemm_fwd(const int32_t *indptr, const int32_t *idx, const float *val,
+                       const float *data, const uint8_t *sel,
+                       int64_t n_rows, int k, int D, const float *deg, float *out)
+{
+    spgemm_fwd_impl(indptr, idx, val, data, sel, 0, n_rows, k, D, deg, out);
+}
+
+void oracle_spgemm_fwd16(const int32_t *indptr, const int32_t *idx, const float *val,
+                         const float *data, const uint16_t *sel,
+                         int64_t n_rows, int k, int D, const float *deg, float *out)
+{
+    spgemm_fwd_impl(indptr, idx, val, data, sel, 1, n_rows, k, D, deg, out);
 }
 
 /*
@@ -205,9 +225,9 @@ void oracle_spgemm_fwd_warp4(const int32_t *warp4, int64_t W, const int32_t *idx
  * Done destination-major through a counting-sort transpose so it is parallel and
  * order-deterministic.
  */
-void oracle_sspmm_bwd(const int32_t *indptr, const int32_t *idx, const float *val,
-                      const float *g, const uint8_t *sel,
-                      int64_t n_rows, int64_t n_cols, int k, int D, const float *deg, float *gs)
+static void sspmm_bwd_impl(const int32_t *indptr, const int32_t *idx, const float *val,
+                           const float *g, const void *sel, int wide,
+                           int64_t n_rows, int64_t n_cols, int k, int D, const float *deg, float *gs)
 {
     int64_t E = indptr[n_rows];
     int64_t *cptr = (int64_t *)calloc((size_t)n_cols + 1, sizeof(int64_t));
@@ -225,7 +245,7 @@ void oracle_sspmm_bwd(const int32_t *indptr, const int32_t *idx, const float *va
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t c = 0; c < n_cols; ++c) {
         for (int l = 0; l < k; ++l) {
-            int s = sel[c * k + l];
+            int s = sel_get(sel, wide, c * k + l);
             double acc = 0.0;
             for (int64_t p = cptr[c]; p < cptr[c + 1]; ++p) {
                 int64_t r = crow[p];
@@ -237,6 +257,20 @@ void oracle_sspmm_bwd(const int32_t *indptr, const int32_t *idx, const float *va
         }
     }
     free(cptr); free(crow); free(cval); free(fill);
+}
+
+void oracle_sspmm_bwd(const int32_t *indptr, const int32_t *idx, const float *val,
+                      const float *g, const uint8_t *sel,
+                      int64_t n_rows, int64_t n_cols, int k, int D, const float *deg, float *gs)
+{
+    sspmm_bwd_impl(indptr, idx, val, g, sel, 0, n_rows, n_cols, k, D, deg, gs);
+}
+
+void oracle_sspmm_bwd16(const int32_t *indptr, const int32_t *idx, const float *val,
+                        const float *g, const uint16_t *sel,
+                        int64_t n_rows, int64_t n_cols, int k, int D, const float *deg, float *gs)
+{
+    sspmm_bwd_impl(indptr, idx, val, g, sel, 1, n_rows, n_cols, k, D, deg, gs);
 }
 
 /*

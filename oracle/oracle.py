@@ -98,6 +98,32 @@ def spgemm_fwd(indptr, indices, values, data, sel, dim=256, deg=None):
     return out
 
 
+def _u16(a):
+    return np.ascontiguousarray(a, dtype=np.uint16)
+
+
+def spgemm_fwd16(indptr, indices, values, data, sel16, dim, deg=None):
+    """Forward with uint16 selectors (feature widths above 256)."""
+    indptr, indices, values, data, sel16 = _i32(indptr), _i32(indices), _f32(values), _f32(data), _u16(sel16)
+    n_rows, k = indptr.size - 1, data.shape[1]
+    out = np.empty((n_rows, dim), np.float32)
+    deg = _f32(deg) if deg is not None else None
+    lib().oracle_spgemm_fwd16(_p(indptr), _p(indices), _p(values), _p(data), _p(sel16), ctypes.c_int64(n_rows),
+                              ctypes.c_int(k), ctypes.c_int(dim), _p(deg), _p(out))
+    return out
+
+
+def sspmm_bwd16(indptr, indices, values, g, sel16, deg=None):
+    indptr, indices, values, g, sel16 = _i32(indptr), _i32(indices), _f32(values), _f32(g), _u16(sel16)
+    n_rows, dim = g.shape
+    n_cols, k = sel16.shape
+    gs = np.empty((n_cols, k), np.float32)
+    deg = _f32(deg) if deg is not None else None
+    lib().oracle_sspmm_bwd16(_p(indptr), _p(indices), _p(values), _p(g), _p(sel16), ctypes.c_int64(n_rows),
+                             ctypes.c_int64(n_cols), ctypes.c_int(k), ctypes.c_int(dim), _p(deg), _p(gs))
+    return gs
+
+
 def spgemm_fwd_warp4(warp4_quads, indices, values, data, sel, n_rows, dim=256):
     warp4_quads, indices, values, data, sel = _i32(warp4_quads), _i32(indices), _f32(values), _f32(data), _u8(sel)
     k = data.shape[1]

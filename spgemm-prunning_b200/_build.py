@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmaxk_b200.so")
-SOURCES = ["topk.cu", "spgemm_fwd.cu", "sspmm_bwd.cu", "meta.cu", "plan.cu"]
+SOURCES = ["topk.cu", "spgemm_fwd.cu", "sspmm_bwd.cu", "meta.cu", "plan.cu", "wide.cu"]
 HEADERS = [os.path.join(CSRC, "maxk_common.cuh"), os.path.join(CSRC, "slots.cuh"), os.path.join(CSRC, "recip31_table.inc"),
            os.path.join(os.path.dirname(HERE), "include", "maxk_b200.h")]
 

@@ -60,8 +60,9 @@ template <int K, int MINB>
 __global__ void __launch_bounds__(kFsThreads, MINB)
 spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ idx, const float *__restrict__ val,
                         const float *__restrict__ cval, const uint8_t *__restrict__ csel, float *__restrict__ out,
-                        int n_edges, int dim, int k, const float *__restrict__ row_div, int ticket_slot)
+                        int n_edges, int dim, int ld_out, int k, const float *__restrict__ row_div, int ticket_slot)
 {
+    const bool vec_out = dim == kAccDim && (ld_out & 7) == 0;     // 32-byte row stores (out is 32-byte aligned)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     float *acc = reinterpret_cast<float *>(smem_raw + (size_t)warp * kSlotWarpBytes);
@@ -191,8 +192,8 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = div_guarded(o[i], dv);
             }
-            float *orow = out + (size_t)r * dim;
-            if (dim == kAccDim) {
+            float *orow = out + (size_t)r * ld_out;
+            if (vec_out) {
                 st_stream_f32x8(orow + 8 * lane, o);
             } else {
 #pragma unroll
@@ -205,7 +206,7 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
             float dv = 1.f;
             const bool has_div = row_div != nullptr && r >= 0;
             if (has_div) dv = __ldg(row_div + r);
-            float *orow = out + (size_t)(r >= 0 ? r : 0) * dim;
+            float *orow = out + (size_t)(r >= 0 ? r : 0) * ld_out;
 #pragma unroll
             for (int n = 0; n < kAccDim / 32; ++n) {
                 const int w0 = (8 * n + 2 * t) * 8 + q;                           // float4 index
@@ -219,7 +220,7 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
                 }
                 if (r >= 0) {
                     const int c0 = 32 * n + 8 * t;
-                    if (dim == kAccDim) {
+                    if (vec_out) {
                         st_stream_f32x8(orow + c0, o);
                     } else {
 #pragma unroll
@@ -250,8 +251,8 @@ static int next_ticket_slot()
 
 template <int K, int MINB>
 static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const float *val, const float *cval,
-                                      const uint8_t *csel, float *out, int n_edges, int dim, int k, const float *row_div,
-                                      cudaStream_t stream)
+                                      const uint8_t *csel, float *out, int n_edges, int dim, int ld_out, int k,
+                                      const float *row_div, cudaStream_t stream)
 {
     const size_t smem = (size_t)kFsWarps * kSlotWarpBytes;
     static LaunchConfig cache[kMaxCachedDevices];
@@ -271,7 +272,7 @@ static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const flo
         cfg.configured = true;
     }
     spgemm_fwd_slots_kernel<K, MINB><<<cfg.sms * cfg.blocks_per_sm, kFsThreads, smem, stream>>>(plan, idx, val, cval, csel,
-                                                                                                out, n_edges, dim, k, row_div, next_ticket_slot());
+                                                                                                out, n_edges, dim, ld_out, k, row_div, next_ticket_slot());
     return cudaGetLastError();
 }
 
@@ -280,25 +281,26 @@ static cudaError_t launch_fwd_slots_b(const int *plan, const int *idx, const flo
 // against 2.62 ms, ogbn-products shape 4.2 ms against 2.6 ms; profiles/r02_slots_lab.txt).
 template <int K>
 static cudaError_t launch_fwd_slots(const int *plan, const int *idx, const float *val, const float *cval,
-                                    const uint8_t *csel, float *out, int n_edges, int dim, int k, const float *row_div,
-                                    cudaStream_t stream)
+                                    const uint8_t *csel, float *out, int n_edges, int dim, int ld_out, int k,
+                                    const float *row_div, cudaStream_t stream)
 {
-    return launch_fwd_slots_b<K, 2>(plan, idx, val, cval, csel, out, n_edges, dim, k, row_div, stream);
+    return launch_fwd_slots_b<K, 2>(plan, idx, val, cval, csel, out, n_edges, dim, ld_out, k, row_div, stream);
 }
 
 }  // namespace maxk
 
 using namespace maxk;
 
-extern "C" int maxk_spgemm_forward_planned(const void *plan, const int32_t *indices, const float *values,
-                                           const float *cbsr_val, const uint8_t *cbsr_sel, float *out, int64_t n_rows,
-                                           int64_t n_edges, int dim, int k, const float *row_div,
-                                           maxk_stream_t stream_)
+// out rows may be strided (ld_out floats apart): the wide-feature path (wide.cu) writes 256-column blocks of a
+// [n_rows, D > 256] matrix in place.
+int maxk_forward_strided(const void *plan, const int32_t *indices, const float *values, const float *cbsr_val,
+                         const uint8_t *cbsr_sel, float *out, int64_t ld_out, int64_t n_rows, int64_t n_edges, int dim,
+                         int k, const float *row_div, cudaStream_t stream)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
     if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
     if (k < 1 || k > kAccDim) return MAXK_ERR_BAD_K;
-    if (n_rows < 0 || n_edges < 0 || n_rows > INT32_MAX - 64 || n_edges > INT32_MAX) return MAXK_ERR_SIZE;
+    if (n_rows < 0 || n_edges < 0 || n_rows > INT32_MAX - 64 || n_edges > INT32_MAX || ld_out < dim || ld_out > INT32_MAX)
+        return MAXK_ERR_SIZE;
     if (n_rows == 0) return MAXK_OK;
     if (!plan || !out) return MAXK_ERR_NULL;
     if (n_edges > 0 && (!indices || !values || !cbsr_val || !cbsr_sel)) return MAXK_ERR_NULL;
@@ -307,17 +309,27 @@ extern "C" int maxk_spgemm_forward_planned(const void *plan, const int32_t *indi
     const bool fast = (k == 8 || k == 16 || k == 32 || k == 64 || k == 96 || k == 128) &&
                       !(((uintptr_t)cbsr_val & 31) | ((uintptr_t)cbsr_sel & 7));
     const int *p = reinterpret_cast<const int *>(plan);
+    const int ld = (int)ld_out;
     cudaError_t err;
     switch (fast ? k : 0) {
-        case 8: err = launch_fwd_slots<8>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
-        case 16: err = launch_fwd_slots<16>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
-        case 32: err = launch_fwd_slots<32>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
-        case 64: err = launch_fwd_slots<64>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
-        case 96: err = launch_fwd_slots<96>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
-        case 128: err = launch_fwd_slots<128>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
-        default: err = launch_fwd_slots<0>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, k, row_div, stream); break;
+        case 8: err = launch_fwd_slots<8>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
+        case 16: err = launch_fwd_slots<16>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
+        case 32: err = launch_fwd_slots<32>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
+        case 64: err = launch_fwd_slots<64>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
+        case 96: err = launch_fwd_slots<96>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
+        case 128: err = launch_fwd_slots<128>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
+        default: err = launch_fwd_slots<0>(p, indices, values, cbsr_val, cbsr_sel, out, (int)n_edges, dim, ld, k, row_div, stream); break;
     }
     return status_from_cuda(err);
+}
+
+extern "C" int maxk_spgemm_forward_planned(const void *plan, const int32_t *indices, const float *values,
+                                           const float *cbsr_val, const uint8_t *cbsr_sel, float *out, int64_t n_rows,
+                                           int64_t n_edges, int dim, int k, const float *row_div,
+                                           maxk_stream_t stream_)
+{
+    return maxk_forward_strided(plan, indices, values, cbsr_val, cbsr_sel, out, dim, n_rows, n_edges, dim, k, row_div,
+                                (cudaStream_t)stream_);
 }
 
 int plan_tail_rows();   // plan.cu

@@ -191,7 +191,7 @@ template <int K>
 __global__ void __launch_bounds__(kBwdThreads, 4)
 sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_end,
                  const int *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ g,
-                 const uint8_t *__restrict__ csel, float *__restrict__ gs, int n_rows, int dim, int k,
+                 const uint8_t *__restrict__ csel, float *__restrict__ gs, int n_rows, int dim, int ld_g, int k,
                  const float *__restrict__ row_div, SchedWorkspace *ws, int *__restrict__ long_rows,
                  int rows_per_grab)
 {
@@ -216,7 +216,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
         float pw = 0.f;
         float pg[kAccDim / 32];
         if (ne > nb && ne - nb <= kLongRow) {
-            load_g_row(g + (size_t)first * dim, dim, pg);
+            load_g_row(g + (size_t)first * ld_g, dim, pg);
             if (BwdLay<K>::LY::kFast && nb + lane < ne) {
                 pc = ld_stream_i32(idx + nb + lane);
                 pw = ld_stream_f32(val + nb + lane);
@@ -236,7 +236,7 @@ sspmm_bwd_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
                 pc = 0;
                 pw = 0.f;
                 if (ne > nb && ne - nb <= kLongRow) {
-                    load_g_row(g + (size_t)(r + 1) * dim, dim, pg);
+                    load_g_row(g + (size_t)(r + 1) * ld_g, dim, pg);
                     if (BwdLay<K>::LY::kFast && nb + lane < ne) {
                         pc = ld_stream_i32(idx + nb + lane);
                         pw = ld_stream_f32(val + nb + lane);
@@ -260,7 +260,7 @@ template <int K>
 __global__ void __launch_bounds__(kBwdLongThreads, 1)
 sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_end,
                       const int *__restrict__ idx, const float *__restrict__ val, const float *__restrict__ g,
-                      const uint8_t *__restrict__ csel, float *__restrict__ gs, int dim, int k,
+                      const uint8_t *__restrict__ csel, float *__restrict__ gs, int dim, int ld_g, int k,
                       const float *__restrict__ row_div, SchedWorkspace *ws, const int *__restrict__ long_rows)
 {
     extern __shared__ __align__(16) float smem[];
@@ -278,7 +278,7 @@ sspmm_bwd_long_kernel(const int *__restrict__ row_begin, const int *__restrict__
         const int b = row_begin[r], e = row_end[r];
         const bool has_div = row_div != nullptr;
         float gv[kAccDim / 32];
-        load_g_row(g + (size_t)r * dim, dim, gv);
+        load_g_row(g + (size_t)r * ld_g, dim, gv);
         stage_row<BwdLay<K>::LK>(gv, gsm, has_div, has_div ? __ldg(row_div + r) : 1.f);
         scatter_row<K, false>(idx, val, csel, gs, gsm, k, b, e, warp, kBwdLongWarps, 0, 0.f);
     }
@@ -298,7 +298,7 @@ static int pick_rows_per_grab(int64_t n_rows, int64_t n_edges, int total_warps)
 template <int K>
 static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const int *idx, const float *val,
                               const float *g, const uint8_t *csel, float *gs, int64_t n_rows, int64_t n_dst,
-                              int64_t n_edges, int dim, int k, const float *row_div, SchedWorkspace *ws,
+                              int64_t n_edges, int dim, int ld_g, int k, const float *row_div, SchedWorkspace *ws,
                               bool zero_fill, cudaStream_t stream)
 {
     const size_t smem_main = (size_t)kBwdWarps * BwdLay<K>::LY::kWords * sizeof(float);
@@ -324,10 +324,10 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
     const int grid = sms * cfg.blocks_per_sm;
     const int rpg = pick_rows_per_grab(n_rows, n_edges, grid * kBwdWarps);
     sspmm_bwd_kernel<K><<<grid, kBwdThreads, smem_main, stream>>>(row_begin, row_end, idx, val, g, csel, gs, (int)n_rows, dim,
-                                                          k, row_div, ws, long_rows, rpg);
+                                                          ld_g, k, row_div, ws, long_rows, rpg);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    sspmm_bwd_long_kernel<K><<<sms, kBwdLongThreads, smem_long, stream>>>(row_begin, row_end, idx, val, g, csel, gs, dim, k,
+    sspmm_bwd_long_kernel<K><<<sms, kBwdLongThreads, smem_long, stream>>>(row_begin, row_end, idx, val, g, csel, gs, dim, ld_g, k,
                                                                   row_div, ws, long_rows);
     return cudaGetLastError();
 }
@@ -336,8 +336,10 @@ static cudaError_t launch_bwd(const int *row_begin, const int *row_end, const in
 
 using namespace maxk;
 
-static int sspmm_backward_impl(bool zero_fill, const int32_t *row_begin, const int32_t *row_end, const int32_t *indices,
-                                   const float *values, const float *g, const uint8_t *cbsr_sel, float *gs,
+// g rows may be strided (ld_g floats apart): the wide-feature path (wide.cu) reads 256-column blocks of a
+// [n_rows, D > 256] gradient in place.
+int maxk_backward_strided(bool zero_fill, const int32_t *row_begin, const int32_t *row_end, const int32_t *indices,
+                                   const float *values, const float *g, int64_t ld_g, const uint8_t *cbsr_sel, float *gs,
                                    int64_t n_rows, int64_t n_dst, int64_t n_edges, int dim, int k,
                                    const float *row_div, void *workspace, size_t workspace_bytes,
                                    maxk_stream_t stream_)
@@ -345,7 +347,8 @@ static int sspmm_backward_impl(bool zero_fill, const int32_t *row_begin, const i
     cudaStream_t stream = (cudaStream_t)stream_;
     if (dim < 1 || dim > kAccDim) return MAXK_ERR_BAD_DIM;
     if (k < 1 || k > kAccDim) return MAXK_ERR_BAD_K;
-    if (n_rows < 0 || n_dst < 0 || n_edges < 0 || n_rows > INT32_MAX || n_edges > INT32_MAX) return MAXK_ERR_SIZE;
+    if (n_rows < 0 || n_dst < 0 || n_edges < 0 || n_rows > INT32_MAX || n_edges > INT32_MAX || ld_g < dim || ld_g > INT32_MAX)
+        return MAXK_ERR_SIZE;
     if (n_dst == 0) return MAXK_OK;
     if (!gs) return MAXK_ERR_NULL;
     if (n_rows == 0 || n_edges == 0)
@@ -358,13 +361,13 @@ static int sspmm_backward_impl(bool zero_fill, const int32_t *row_begin, const i
     SchedWorkspace *ws = reinterpret_cast<SchedWorkspace *>(workspace);
     cudaError_t err;
     switch (k) {
-        case 8: err = launch_bwd<8>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
-        case 16: err = launch_bwd<16>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
-        case 32: err = launch_bwd<32>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
-        case 64: err = launch_bwd<64>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
-        case 96: err = launch_bwd<96>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
-        case 128: err = launch_bwd<128>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
-        default: err = launch_bwd<0>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, k, row_div, ws, zero_fill, stream); break;
+        case 8: err = launch_bwd<8>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
+        case 16: err = launch_bwd<16>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
+        case 32: err = launch_bwd<32>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
+        case 64: err = launch_bwd<64>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
+        case 96: err = launch_bwd<96>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
+        case 128: err = launch_bwd<128>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
+        default: err = launch_bwd<0>(row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim, (int)ld_g, k, row_div, ws, zero_fill, stream); break;
     }
     return status_from_cuda(err);
 }
@@ -375,8 +378,8 @@ extern "C" int maxk_sspmm_backward(const int32_t *row_begin, const int32_t *row_
                                    const float *row_div, void *workspace, size_t workspace_bytes,
                                    maxk_stream_t stream)
 {
-    return sspmm_backward_impl(true, row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim,
-                               k, row_div, workspace, workspace_bytes, stream);
+    return maxk_backward_strided(true, row_begin, row_end, indices, values, g, dim, cbsr_sel, gs, n_rows, n_dst, n_edges, dim,
+                                 k, row_div, workspace, workspace_bytes, stream);
 }
 
 extern "C" int maxk_sspmm_backward_accumulate(const int32_t *row_begin, const int32_t *row_end,
@@ -385,6 +388,6 @@ extern "C" int maxk_sspmm_backward_accumulate(const int32_t *row_begin, const in
                                               int64_t n_edges, int dim, int k, const float *row_div, void *workspace,
                                               size_t workspace_bytes, maxk_stream_t stream)
 {
-    return sspmm_backward_impl(false, row_begin, row_end, indices, values, g, cbsr_sel, gs, n_rows, n_dst, n_edges, dim,
-                               k, row_div, workspace, workspace_bytes, stream);
+    return maxk_backward_strided(false, row_begin, row_end, indices, values, g, dim, cbsr_sel, gs, n_rows, n_dst, n_edges, dim,
+                                 k, row_div, workspace, workspace_bytes, stream);
 }

@@ -47,6 +47,12 @@ _SIGNATURES = {
                                      _c_int, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_sspmm_backward_accumulate": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64,
                                                 _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
+    "maxk_topk_cbsr16": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
+    "maxk_wide_workspace_bytes": (_c_size, [_c_i64, _c_i64, _c_int, _c_int]),
+    "maxk_spgemm_forward16": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_int, _c_int,
+                                       _c_ptr, _c_ptr, _c_size, _c_ptr]),
+    "maxk_sspmm_backward16": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64, _c_int,
+                                       _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_spgemm_workspace_bytes": (_c_size, [_c_i64]),
     "maxk_plan_bytes": (_c_size, [_c_i64]),
     "maxk_plan_workspace_bytes": (_c_size, [_c_i64]),
@@ -338,6 +344,107 @@ def topk_cbsr(x, k, order=ORDER_BANKED, want_sel=True, want_i32=False, want_i64=
         _status(_lib.maxk_topk_cbsr(_ptr(x), n, d, k, order, _ptr(vals), _ptr(sel), _ptr(i32), _ptr(i64),
                                     _ptr(masked), _stream(x)), "maxk_topk_cbsr")
     return {"values": vals, "sel": sel, "i32": i32, "i64": i64, "masked": masked}
+
+
+# ----------------------------------------------------------------------------------------------
+# Feature widths above 256: uint16 selectors (csrc/wide.cu).  torch has no uint16 arithmetic, so the selector
+# tensors are int16 views of the same bits (use .view(torch.uint16) / .to(torch.int32) & 0xffff to read them).
+# ----------------------------------------------------------------------------------------------
+WIDE_MAX_DIM = 1024
+
+
+def topk_cbsr16(x, k, want_masked=False):
+    """Exact row-wise top-k of x[N, D <= 1024] -> dict(values fp32 [N, k], sel16 int16-typed uint16 bits [N, k] in
+    column-ascending order, masked [N, D] or None)."""
+    x = _cuda(x, "input", torch.float32)
+    _check(x.dim() == 2, "Input must be 2D tensor")
+    n, d = x.shape
+    _check(0 < k <= min(d, FULL_DIM), "Invalid k value (1 <= k <= min(D, 256))")
+    _check(d <= WIDE_MAX_DIM, "feature dim must be <= 1024")
+    vals = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    sel = torch.empty((n, k), dtype=torch.int16, device=x.device)
+    masked = torch.empty_like(x) if want_masked else None
+    with torch.cuda.device(x.device):
+        _status(_lib.maxk_topk_cbsr16(_ptr(x), n, d, int(k), _ptr(vals), _ptr(sel), _ptr(masked), _stream(x)), "maxk_topk_cbsr16")
+    return {"values": vals, "sel16": sel, "masked": masked}
+
+
+def _wide_workspace(n_rows, n_src, dim, k, device):
+    nbytes = _lib.maxk_wide_workspace_bytes(n_rows, n_src, dim, k)
+    return torch.empty(nbytes + 256, dtype=torch.uint8, device=device), nbytes
+
+
+def spgemm_forward16_csr(row_begin, row_end, indices, values, cbsr_val, cbsr_sel16, dim, row_div=None, plan=None):
+    """out[n_rows, dim] = A_csr x scatter(CBSR with uint16 selectors), optionally / row_div."""
+    row_begin = _cuda(row_begin, "row_begin", torch.int32)
+    row_end = _cuda(row_end, "row_end", torch.int32)
+    indices = _cuda(indices, "indices", torch.int32)
+    values = _cuda(values, "values", torch.float32)
+    cbsr_val = _cuda(cbsr_val, "input_data", torch.float32)
+    cbsr_sel16 = _cuda(cbsr_sel16, "sparse_selector", torch.int16)
+    _check(cbsr_val.dim() == 2 and cbsr_sel16.shape == cbsr_val.shape, "input_data / sparse_selector must both be [N, k]")
+    n_rows, (n_src, k) = row_begin.numel(), cbsr_val.shape
+    _check(0 < dim <= WIDE_MAX_DIM, "dim must be in [1, 1024]")
+    if row_div is not None:
+        row_div = _cuda(row_div, "row_div", torch.float32)
+    if plan is None:
+        plan = build_plan(row_begin, row_end)
+    _check(plan.n_rows == n_rows, "plan was built for another row structure")
+    _check_graph(indices, n_src, row_end, "spgemm_forward16")
+    out = torch.empty((n_rows, dim), dtype=torch.float32, device=cbsr_val.device)
+    with torch.cuda.device(cbsr_val.device):
+        ws, ws_bytes = _wide_workspace(n_rows, n_src, dim, k, cbsr_val.device)
+        _status(_lib.maxk_spgemm_forward16(_ptr(plan.buf), _ptr(indices), _ptr(values), _ptr(cbsr_val), _ptr(cbsr_sel16), _ptr(out),
+                                           n_rows, n_src, indices.numel(), int(dim), k, _ptr(row_div), _ptr(ws), ws_bytes,
+                                           _stream(cbsr_val)), "maxk_spgemm_forward16")
+    return out
+
+
+def sspmm_backward16_csr(row_begin, row_end, indices, values, grad_output, cbsr_sel16, row_div=None):
+    """gs[n_dst, k] = sample_sel(A_csr^T (grad_output / row_div)) for uint16 selectors, grad_output [n_rows, D <= 1024]."""
+    row_begin = _cuda(row_begin, "row_begin", torch.int32)
+    row_end = _cuda(row_end, "row_end", torch.int32)
+    indices = _cuda(indices, "indices", torch.int32)
+    values = _cuda(values, "values", torch.float32)
+    grad_output = _cuda(grad_output, "grad_output", torch.float32)
+    cbsr_sel16 = _cuda(cbsr_sel16, "sparse_selector", torch.int16)
+    n_rows, dim = row_begin.numel(), grad_output.size(1)
+    n_dst, k = cbsr_sel16.shape
+    _check(grad_output.size(0) == n_rows and dim <= WIDE_MAX_DIM, "grad_output must be [n_rows, D <= 1024]")
+    if row_div is not None:
+        row_div = _cuda(row_div, "row_div", torch.float32)
+    _check_graph(indices, n_dst, row_end, "sspmm_backward16")
+    gs = torch.empty((n_dst, k), dtype=torch.float32, device=grad_output.device)
+    with torch.cuda.device(grad_output.device):
+        ws, ws_bytes = _wide_workspace(n_rows, n_dst, dim, k, grad_output.device)
+        _status(_lib.maxk_sspmm_backward16(_ptr(row_begin), _ptr(row_end), _ptr(indices), _ptr(values), _ptr(grad_output),
+                                           _ptr(cbsr_sel16), _ptr(gs), n_rows, n_dst, indices.numel(), dim, k, _ptr(row_div),
+                                           _ptr(ws), ws_bytes, _stream(grad_output)), "maxk_sspmm_backward16")
+    return gs
+
+
+class WideMaxKSpGEMMFunction(torch.autograd.Function):
+    """x[N, D in (256, 1024]] -> A @ maxk(x) / in_degrees with gradients to x: the generation-1 operator
+    (maxk_spgemm_function.py) for feature widths its uint8 selectors cannot address."""
+
+    @staticmethod
+    def forward(ctx, indptr, indices, values, x, k, in_degrees=None, out_degrees=None):
+        row_begin, row_end, plan = plan_for_indptr(indptr)
+        r = topk_cbsr16(x, int(k))
+        ctx.save_for_backward(row_begin, row_end, indices, values, r["sel16"],
+                              out_degrees if out_degrees is not None else torch.empty(0, device=x.device))
+        ctx.has_div, ctx.dim = out_degrees is not None, x.size(1)
+        return spgemm_forward16_csr(row_begin, row_end, indices, values, r["values"], r["sel16"], x.size(1),
+                                    row_div=in_degrees, plan=plan)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        row_begin, row_end, indices, values, sel16, out_degrees = ctx.saved_tensors
+        gs = sspmm_backward16_csr(row_begin, row_end, indices, values, grad_output.contiguous(), sel16,
+                                  row_div=out_degrees if ctx.has_div else None)
+        grad_x = torch.zeros(gs.size(0), ctx.dim, dtype=gs.dtype, device=gs.device)
+        grad_x.scatter_(1, sel16.to(torch.int64) & 0xffff, gs)
+        return None, None, None, grad_x, None, None, None
 
 
 MAX_PEERS = 8

@@ -161,16 +161,21 @@ def test_v2_operator_generations(module):
         torch.testing.assert_close(tv.grad.cpu(), torch.from_numpy(gs), rtol=2e-5, atol=1e-6)
 
 
-def test_training_step_gradients_at_the_yelp_shape():
-    """BASELINE.json config 3 (Yelp-shape GCN, MaxK k = 32, hidden 256, 3 layers): loss and every parameter gradient
-    of ONE full-graph training step against the torch restatement (torch.topk + scatter + torch.sparse mm) at the
-    full graph size (716,847 nodes, ~14 M edges)."""
+@pytest.mark.parametrize("layers", [1, 3])
+def test_training_step_gradients_at_the_yelp_shape(layers):
+    """BASELINE.json config 3 (Yelp-shape GCN, MaxK k = 32, hidden 256): loss, logits and every parameter gradient of
+    ONE full-graph training step against the torch restatement (torch.topk + scatter + torch.sparse mm) at the full
+    graph size (716,847 nodes, ~14 M edges).
+    One hidden layer: both sides select from bit-identical inputs, so everything must agree to rounding.
+    Three layers (the configuration of scripts_train/yelp_maxk.sh): a 1e-7 rounding difference in layer i can flip a
+    near-tie of layer i+1's top-k, which changes that node's row discretely on either side -- the comparison is then
+    statistical: the loss agrees, and all but a small fraction of the logits do."""
     from maxk_gnn_training import synthetic_task
     from maxk_models_integrated import MaxKGCN
     torch.manual_seed(0)
     gc, x, y, masks = synthetic_task("yelp", 1.0, 128, 16, torch.device("cuda"))
     n, k = gc.num_nodes(), 32
-    model = MaxKGCN(128, 256, 3, 16, maxk=k, feat_drop=0.0, norm=True, graph_name="yelp").cuda()
+    model = MaxKGCN(128, 256, layers, 16, maxk=k, feat_drop=0.0, norm=True, graph_name="yelp").cuda()
     lossf = torch.nn.functional.binary_cross_entropy_with_logits
     out = model(gc, x)
     loss = lossf(out[masks[0]], y[masks[0]])
@@ -187,8 +192,18 @@ def test_training_step_gradients_at_the_yelp_shape():
     ref = model.lin_out(h)
     ref_loss = lossf(ref[masks[0]], y[masks[0]])
     ref_loss.backward()
-    torch.testing.assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-4)
-    for name, p in model.named_parameters():
-        if p.grad is not None:
-            torch.testing.assert_close(grads[name], p.grad, rtol=5e-3, atol=1e-6, msg=lambda m, n=name: n + ": " + m)
+    if layers == 1:
+        torch.testing.assert_close(loss, ref_loss, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-4)
+        for name, p in model.named_parameters():
+            if p.grad is not None:
+                scale = float(p.grad.abs().max())
+                torch.testing.assert_close(grads[name], p.grad, rtol=5e-3, atol=1e-4 * scale, msg=lambda m, n=name: n + ": " + m)
+    else:
+        torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=1e-6)
+        bad = ((out - ref).abs() > 1e-4 + 1e-3 * ref.abs()).float().mean().item()
+        assert bad < 0.01, "fraction of logits outside tolerance: %.4f" % bad
+        for name, p in model.named_parameters():
+            if p.grad is not None:
+                rel = float((grads[name] - p.grad).norm() / p.grad.norm().clamp(min=1e-30))
+                assert rel < 2e-2, "%s: relative gradient difference %.3e" % (name, rel)
