@@ -517,7 +517,8 @@ def run_ours(args, n, e):
                             "traffic": prof.get("spgemm_fwd_kernel"),
                             "layer_frac": value / peak,
                             "note": "not HBM-limited: the kernel saturates the SM LSU data pipe "
-                                    "(l1tex__data_pipe_lsu_wavefronts ~91% of peak), see profiles/ and DESIGN.md",
+                                    "(l1tex__data_pipe_lsu_wavefronts %s%% of peak in the committed ncu capture), see "
+                                    "roofline.l2, profiles/ and DESIGN.md 3.1-3.2" % prof.get("fwd_lsu_pct_of_peak", "~96"),
                             "l2": {"what": "the roofline this kernel is actually on: every edge gathers a 160-byte CBSR row "
                                            "out of L2 and scatters 32 products into shared memory",
                                    "gathered_bytes_per_launch": gathered,

@@ -1,44 +1,54 @@
-"""Developer tool: shared-memory wavefronts per edge of the forward accumulate (and backward look-up) for a CBSR
-entry order, under the conflict model measured on B200: one LDS/STS warp instruction costs
-as many wavefronts as its worst bank multiplicity.  Pure numpy, no GPU.
+"""Developer tool: shared-memory wavefronts per edge of the forward accumulate for a CBSR entry order and a
+slot layout, under the conflict model measured on B200: one LDS/STS warp instruction costs as
+many wavefronts as its worst bank multiplicity.  Pure numpy, no GPU.
 
     python tools/bank_conflict_sim.py
 
-Layout of Lay<K> (csrc/maxk_common.cuh): a lane owns EPL consecutive entries of one edge, L = k / EPL lanes cover
-an edge, EPI = 32 / L edges are processed per warp instruction, every edge slot has its own copy of the 256
-columns in banks [q L, q L + L): inside a slot, instruction i touches the entries {EPL t + i : t < L}, and two of
-them collide when their columns are equal mod L.  The instruction costs the worst slot.
+Layout (csrc/slots.cuh): L lanes cover an edge, a lane owns EPL = k / L entries, S = 32 / L edge slots per warp
+instruction, every slot has its own copy of the 256 columns in banks [q L, q L + L).  Inside a slot, instruction i
+touches the i-th entry of each of the L lanes, and two of them collide when their columns are equal mod L; the
+instruction costs the worst slot.  Orders: "random" (the selection in arbitrary order), "plain" = sorted by
+(column mod L, column), "by size" = residue classes with the largest class first (MAXK_ORDER_BANKED for L = 4): a
+class with more than EPL entries necessarily puts two of them into some instruction; starting with the largest class
+makes those doubled instructions the SAME (first) ones in all slots, so the worst-slot cost is paid once.
 """
 import numpy as np
 
 
-def wavefronts_per_edge(rows, k):
-    epl = 2 if k == 8 else 4
-    lanes = k // epl
-    epi = 32 // lanes
-    n = (len(rows) // epi) * epi
-    res = rows[:n] % lanes                                   # bank residue of every entry
-    res = res.reshape(n, lanes, epl)                          # [edge, lane t, entry i of the lane]
+def wavefronts_per_edge(rows, lanes):
+    k = rows.shape[1]
+    epl = k // lanes
+    slots = 32 // lanes
+    n = (len(rows) // slots) * slots
+    res = (rows[:n] % lanes).reshape(n, lanes, epl)             # [edge, lane t, entry i of the lane]
     mult = np.zeros((n, epl), np.int64)
     for i in range(epl):
         counts = np.zeros((n, lanes), np.int64)
         np.add.at(counts, (np.repeat(np.arange(n), lanes), res[:, :, i].reshape(-1)), 1)
-        mult[:, i] = counts.max(axis=1)                       # worst bank of this slot in instruction i
-    per_group = mult.reshape(n // epi, epi, epl).max(axis=1).sum(axis=1)   # worst slot per instruction, summed
-    return 2.0 * per_group.mean() / epi                       # read + write, per edge
+        mult[:, i] = counts.max(axis=1)                        # worst bank of this slot in instruction i
+    per_group = mult.reshape(n // slots, slots, epl).max(axis=1).sum(axis=1)   # worst slot per instruction, summed
+    return 2.0 * per_group.mean() / slots                      # read + write, per edge
+
+
+def by_size(row, m):
+    cls = [[c for c in sorted(row) if c % m == j] for j in range(m)]
+    cls.sort(key=lambda l: -len(l))                            # stable: ties keep the lower class first
+    return np.array([c for l in cls for c in l])
 
 
 def main():
     rng = np.random.default_rng(0)
-    print("%4s %28s %10s %10s %10s" % ("k", "layout", "no-conflict", "value order", "banked"))
-    for k, m in ((8, 4), (16, 4), (32, 8), (64, 16)):
-        cols = np.stack([rng.choice(256, k, replace=False) for _ in range(20000)])
-        banked = np.stack([np.array(sorted(r, key=lambda c: (c % m, c))) for r in cols])
-        epl = 2 if k == 8 else 4
-        lanes = k // epl
-        print("%4d %28s %10.2f %10.2f %10.2f" % (k, "%d slots x %d banks, %d entries/lane" % (32 // lanes, lanes, epl),
-                                                  2.0 * epl / (32 // lanes), wavefronts_per_edge(cols, k),
-                                                  wavefronts_per_edge(banked, k)))
+    print("%4s %22s %8s %8s %8s %8s" % ("k", "layout", "floor", "random", "plain", "by size"))
+    for k in (8, 16, 32, 64, 128):
+        cols = np.stack([rng.choice(256, k, replace=False) for _ in range(8000)])
+        for lanes in (4, 8, 16):
+            if k // lanes < 1 or (k == 8 and lanes == 16):
+                continue
+            plain = np.stack([np.array(sorted(r, key=lambda c: (c % lanes, c))) for r in cols])
+            sized = np.stack([by_size(r, lanes) for r in cols])
+            print("%4d %22s %8.2f %8.2f %8.2f %8.2f" % (k, "%d slots x %d banks" % (32 // lanes, lanes), 2.0 * k / 32,
+                                                        wavefronts_per_edge(cols, lanes), wavefronts_per_edge(plain, lanes),
+                                                        wavefronts_per_edge(sized, lanes)))
 
 
 if __name__ == "__main__":
