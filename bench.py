@@ -429,6 +429,30 @@ def run_ours(args, n, e):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_step = float(t.item())
 
+        # phase split of the step (outside the timed region; max over ranks): top-k + exchange, forward kernel,
+        # backward (kernel + exchange), backward kernel alone
+        phases = None
+        if args.phases:
+            marks = [[_ev() for _ in range(5)] for _ in range(10)]
+            ipl = layer.rows["indptr"]
+            scratch = torch.empty(layer.world * m, k, device=dev)
+            for mk in marks:
+                mk[0].record()
+                vf, sf, _ = layer.gather_cbsr(x)
+                layer.sel_full = sf
+                mk[1].record()
+                layer.compute.spgemm(layer.rows, vf, sf, layer.row_div)
+                mk[2].record()
+                layer.backward(grad)
+                mk[3].record()
+                K.sspmm_backward_csr(ipl[:-1], ipl[1:], layer.rows["indices"], layer.rows["values"], grad, sf, out=scratch)
+                mk[4].record()
+            torch.cuda.synchronize()
+            ph = torch.tensor([sum(mk[i].elapsed_time(mk[i + 1]) for mk in marks) / len(marks) for i in range(4)], device=dev)
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+            phases = dict(zip(("topk_and_exchange_ms", "fwd_kernel_ms", "bwd_total_ms", "bwd_kernel_ms"), ph.tolist()))
+            del scratch
+
         if not args.no_parity:
             # every rank checks sampled rows of ITS output slabs against the oracle on the whole problem
             # (features, gradients and CBSR all-gathered outside the timed region; the full graph is still resident)
@@ -483,10 +507,12 @@ def run_ours(args, n, e):
         t_e2e = float(t.item())
         h2d, d2h = world * 2 * m * DIM * 4, world * (m * DIM * 4 + m * k * 4)
         launches = KERNELS_PER_STEP * args.steps * world
-        parts = {"wire_bytes_per_rank": layer.wire_bytes(), "forward_exchange": layer.gather,
+        parts = {"wire_bytes_per_rank": layer.wire_bytes(), "forward_exchange": layer.gather, "backward_exchange": layer.reduce,
                  "forward_exchange_fallback_reason": layer.gather_error,
                  "e2e_note": "per rank: 4 row chunks, h2d / compute+NCCL / d2h on three streams, steps double-buffered; "
                              "process bound to the %d cores next to its GPU" % host_cores}
+        if phases:
+            parts["phases"] = phases
         roof_bytes, roof_ms = None, None
         scaling = "strong"
 
@@ -554,6 +580,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check after the timed region")
     ap.add_argument("--no-sweep", action="store_true", help="skip the secondary configurations (extra.sweep)")
+    ap.add_argument("--phases", action="store_true", help="multi-GPU: add a per-phase split of the step to breakdown")
     ap.add_argument("--kind", default="uniform", choices=["uniform", "powerlaw"], help="degree distribution of the synthetic graph")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU forward exchange: top-k writing into peer memory, or NCCL all_gather")

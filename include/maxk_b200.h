@@ -88,11 +88,20 @@ int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, int order,
  * rank's own buffer included; peer-mapped memory, e.g. torch symmetric memory or cudaIpc mappings).  Replaces
  * local top-k + two all_gather launches; the caller synchronises the ranks afterwards (one barrier).
  * dim is 256, order MAXK_ORDER_BANKED, k in {8, 16, 32, 64, 96, 128}; x (and masked, nullable) 32-byte aligned.
+ * mc_val / mc_sel (nullable): NVLS multicast mappings of the same two buffers; when given, every row is written
+ * with ONE multimem.st per 4 bytes and the NVSwitch replicates it to all ranks (egress 5k bytes per node instead
+ * of P times that).
+ * maxk_nvls_reduce: dst[i] = sum over the ranks of the multicast group of src_rank[i] (multimem.ld_reduce, the
+ * sum is formed inside the switch): the backward's reduce_scatter of the partial sampled gradients, each rank
+ * reducing its own slab.  mc_src is a multicast address, n_floats a multiple of 4, both pointers 16-byte aligned;
+ * the caller synchronises the ranks before (all partials complete) as for any collective.
  */
 #define MAXK_MAX_PEERS 8
 int maxk_topk_cbsr_peers(const float *x, int64_t n_rows, int k, int n_peers,
-                         float *const *peer_val, uint8_t *const *peer_sel, int64_t row_offset,
+                         float *const *peer_val, uint8_t *const *peer_sel,
+                         float *mc_val, uint8_t *mc_sel, int64_t row_offset,
                          float *masked, maxk_stream_t stream);
+int maxk_nvls_reduce(const float *mc_src, float *dst, int64_t n_floats, maxk_stream_t stream);
 
 /*
  * (2) Forward row-wise-product SpGEMM: out = A_csr x scatter(CBSR)   (optionally / row_div).

@@ -324,7 +324,14 @@ struct PeerOut {
     int n;                         // 0: plain local output
     float *val[MAXK_MAX_PEERS];    // already offset to this rank's first row
     uint8_t *sel[MAXK_MAX_PEERS];
+    float *mc_val;                 // NVLS multicast mappings of the same buffers (nullable): ONE store reaches all ranks
+    uint32_t *mc_sel;
 };
+
+__device__ __forceinline__ void multimem_st_b32(void *mc, uint32_t bits)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(__uint_as_float(bits)) : "memory");
+}
 
 template <int K>
 __global__ void __launch_bounds__(kTopkThreads)
@@ -451,6 +458,8 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
                 if (peers.n == 0) {
                     out_val[o] = __uint_as_float(ent.x);
                     if (out_sel) out_sel[o] = (uint8_t)c;
+                } else if (peers.mc_val != nullptr) {
+                    multimem_st_b32(peers.mc_val + o, ent.x);       // the switch replicates the store to every rank
                 } else {
                     for (int p = 0; p < peers.n; ++p) {
                         peers.val[p][o] = __uint_as_float(ent.x);
@@ -461,7 +470,27 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
                 if (out_i64) out_i64[o] = c;
             }
         }
+        if (peers.n != 0 && peers.mc_val != nullptr && lane < K / 4) {   // selectors: 4 per 32-bit multicast store
+            uint32_t w = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) w |= (ent_w[2 * (4 * lane + b) + 1] & 0xffu) << (8 * b);
+            multimem_st_b32(peers.mc_sel + (r * K) / 4 + lane, w);
+        }
         __syncwarp();
+    }
+}
+
+// out[i] = sum over the ranks of the multicast group of their buffers at the same offset, reduced inside the
+// NVSwitch (multimem.ld_reduce, SASS LDGMC.ADD): the backward's reduce_scatter of the partial sampled gradient.
+__global__ void __launch_bounds__(kTopkThreads)
+nvls_reduce_kernel(const float *__restrict__ mc_src, float *__restrict__ dst, int64_t n_vec4)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += stride) {
+        float4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_src + 4 * i) : "memory");
+        reinterpret_cast<float4 *>(dst)[i] = v;
     }
 }
 
@@ -628,6 +657,8 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
         // the layer's hot configurations (32-byte loads need 32-byte aligned rows)
         PeerOut none;
         none.n = 0;
+        none.mc_val = nullptr;
+        none.mc_sel = nullptr;
         return status_from_cuda(dispatch_topk_banked(k, x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, none));
     }
 #define MAXK_TOPK_LAUNCH(D256, ORD) \
@@ -645,8 +676,22 @@ extern "C" int maxk_topk_cbsr(const float *x, int64_t n_rows, int dim, int k, in
     return status_from_cuda(cudaGetLastError());
 }
 
+extern "C" int maxk_nvls_reduce(const float *mc_src, float *dst, int64_t n_floats, maxk_stream_t stream)
+{
+    if (n_floats < 0 || (n_floats & 3)) return MAXK_ERR_SIZE;
+    if (n_floats == 0) return MAXK_OK;
+    if (!mc_src || !dst) return MAXK_ERR_NULL;
+    if (((uintptr_t)mc_src | (uintptr_t)dst) & 15) return MAXK_ERR_ALIGN;
+    const int64_t n4 = n_floats / 4;
+    const int64_t need = (n4 + kTopkThreads - 1) / kTopkThreads;
+    const int64_t cap = (int64_t)device_sm_count() * 8;
+    nvls_reduce_kernel<<<(int)(need < cap ? need : cap), kTopkThreads, 0, (cudaStream_t)stream>>>(mc_src, dst, n4);
+    return status_from_cuda(cudaGetLastError());
+}
+
 extern "C" int maxk_topk_cbsr_peers(const float *x, int64_t n_rows, int k, int n_peers, float *const *peer_val,
-                                    uint8_t *const *peer_sel, int64_t row_offset, float *masked, maxk_stream_t stream)
+                                    uint8_t *const *peer_sel, float *mc_val, uint8_t *mc_sel, int64_t row_offset,
+                                    float *masked, maxk_stream_t stream)
 {
     if (banked_modulus(k) < 4) return MAXK_ERR_BAD_K;
     if (n_rows < 0 || row_offset < 0) return MAXK_ERR_SIZE;
@@ -661,6 +706,10 @@ extern "C" int maxk_topk_cbsr_peers(const float *x, int64_t n_rows, int k, int n
         peers.val[p] = peer_val[p] + row_offset * k;
         peers.sel[p] = peer_sel[p] + row_offset * k;
     }
+    const bool mc = mc_val != nullptr && mc_sel != nullptr;
+    if (mc && (((uintptr_t)mc_val | (uintptr_t)mc_sel) & 3)) return MAXK_ERR_ALIGN;
+    peers.mc_val = mc ? mc_val + row_offset * k : nullptr;
+    peers.mc_sel = mc ? reinterpret_cast<uint32_t *>(mc_sel + row_offset * k) : nullptr;
     return status_from_cuda(dispatch_topk_banked(k, x, n_rows, nullptr, nullptr, nullptr, nullptr, masked,
                                                  (cudaStream_t)stream, peers));
 }

@@ -40,7 +40,8 @@ _SIGNATURES = {
     "maxk_status_string": (ctypes.c_char_p, [_c_int]),
     "maxk_banked_modulus": (_c_int, [_c_int]),
     "maxk_topk_cbsr": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr]),
-    "maxk_topk_cbsr_peers": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_i64, _c_ptr, _c_ptr]),
+    "maxk_topk_cbsr_peers": (_c_int, [_c_ptr, _c_i64, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_ptr, _c_ptr]),
+    "maxk_nvls_reduce": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_ptr]),
     "maxk_spgemm_forward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_int,
                                      _c_int, _c_ptr, _c_ptr, _c_size, _c_ptr]),
     "maxk_sspmm_backward": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_i64, _c_i64,
@@ -450,9 +451,10 @@ class WideMaxKSpGEMMFunction(torch.autograd.Function):
 MAX_PEERS = 8
 
 
-def topk_cbsr_to_peers(x, k, peer_val_ptrs, peer_sel_ptrs, row_offset, want_masked=False):
+def topk_cbsr_to_peers(x, k, peer_val_ptrs, peer_sel_ptrs, row_offset, want_masked=False, mc_val_ptr=0, mc_sel_ptr=0):
     """Row-sharded top-k: row r of x -> row (row_offset + r) of every peer's gathered CBSR buffers (raw device
-    pointers of peer-mapped [P*m, k] fp32 / uint8 buffers, own rank included).  Returns the masked rows or None."""
+    pointers of peer-mapped [P*m, k] fp32 / uint8 buffers, own rank included; mc_*_ptr: their NVLS multicast
+    mappings, 0 = none).  Returns the masked rows or None."""
     x = _cuda(x, "input", torch.float32)
     _check(x.dim() == 2 and x.size(1) == FULL_DIM, "the peer-writing top-k needs [rows, 256] features")
     _check(len(peer_val_ptrs) == len(peer_sel_ptrs) and 1 <= len(peer_val_ptrs) <= MAX_PEERS, "1..8 peers")
@@ -461,9 +463,20 @@ def topk_cbsr_to_peers(x, k, peer_val_ptrs, peer_sel_ptrs, row_offset, want_mask
     ps = (ctypes.c_void_p * len(peer_sel_ptrs))(*[int(p) for p in peer_sel_ptrs])
     masked = torch.empty_like(x) if want_masked else None
     with torch.cuda.device(x.device):
-        _status(_lib.maxk_topk_cbsr_peers(_ptr(x), n, int(k), len(peer_val_ptrs), pv, ps, int(row_offset), _ptr(masked),
-                                          _stream(x)), "maxk_topk_cbsr_peers")
+        _status(_lib.maxk_topk_cbsr_peers(_ptr(x), n, int(k), len(peer_val_ptrs), pv, ps, _c_ptr(int(mc_val_ptr)),
+                                          _c_ptr(int(mc_sel_ptr)), int(row_offset), _ptr(masked), _stream(x)),
+                "maxk_topk_cbsr_peers")
     return masked
+
+
+def nvls_reduce(mc_src_ptr, dst):
+    """dst[...] = sum over the ranks of the multicast group of their buffers at mc_src_ptr (a raw multicast address),
+    reduced inside the NVSwitch."""
+    _check(dst.is_cuda and dst.is_contiguous() and dst.dtype == torch.float32 and dst.numel() % 4 == 0,
+           "dst must be a contiguous fp32 CUDA tensor with a multiple of 4 elements")
+    with torch.cuda.device(dst.device):
+        _status(_lib.maxk_nvls_reduce(_c_ptr(int(mc_src_ptr)), _ptr(dst), dst.numel(), _stream(dst)), "maxk_nvls_reduce")
+    return dst
 
 
 def cbsr_scatter(vals, sel, dim=FULL_DIM):

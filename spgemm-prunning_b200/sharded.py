@@ -190,12 +190,47 @@ class CudaCompute:
         return self.k.sspmm_backward_csr(ip[:-1], ip[1:], g["indices"], g["values"], grad, sel, row_div=row_div)
 
 
+def _multicast_ptr(handle):
+    """NVLS multicast address of a symmetric-memory allocation, or 0 when the system has none."""
+    try:
+        if not handle.has_multicast_support:
+            return 0
+        return int(handle.multicast_ptr or 0)
+    except Exception:
+        return 0
+
+
+class PeerReduce:
+    """The backward's partial sampled gradient [P*m, k] in symmetric memory, two sets (call c uses set c % 2): after
+    one barrier every rank sums ITS slab over all ranks with multimem.ld_reduce -- the reduction happens inside the
+    NVSwitch, a rank receives m*k*4 bytes instead of reading (P-1) slabs.  The barrier of call c+1 orders every
+    rank's read of set c % 2 before anybody zero-fills it again in call c+2."""
+
+    def __init__(self, rows_total, k, device, group):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.sets = []
+        for _ in range(2):
+            buf = symm.empty((rows_total, k), dtype=torch.float32, device=device)
+            h = symm.rendezvous(buf, pg)
+            mc = _multicast_ptr(h)
+            if not mc:
+                raise RuntimeError("no NVLS multicast mapping for symmetric memory on this system")
+            self.sets.append({"buf": buf, "h": h, "mc": mc})
+        self.call = 0
+
+    def next_set(self):
+        s = self.sets[self.call % 2]
+        self.call += 1
+        return s
+
+
 class PeerGather:
     """Gathered CBSR buffers [P*m, k] in torch symmetric memory (peer-mapped over NVLink), two sets: step s uses
     set s % 2.  One barrier per step (after the peer writes) is enough: a rank can only be one barrier ahead of
     the slowest one, so nobody writes set s % 2 again before every rank has finished reading it."""
 
-    def __init__(self, rows_total, k, device, group):
+    def __init__(self, rows_total, k, device, group, use_multicast=True):
         import torch.distributed._symmetric_memory as symm
         pg = group if group is not None else dist.group.WORLD
         self.sets = []
@@ -203,8 +238,11 @@ class PeerGather:
             vals = symm.empty((rows_total, k), dtype=torch.float32, device=device)
             sel = symm.empty((rows_total, k), dtype=torch.uint8, device=device)
             hv, hs = symm.rendezvous(vals, pg), symm.rendezvous(sel, pg)
+            mc = use_multicast and _multicast_ptr(hv) and _multicast_ptr(hs)
             self.sets.append({"vals": vals, "sel": sel, "hv": hv, "hs": hs,
-                              "val_ptrs": list(hv.buffer_ptrs), "sel_ptrs": list(hs.buffer_ptrs)})
+                              "val_ptrs": list(hv.buffer_ptrs), "sel_ptrs": list(hs.buffer_ptrs),
+                              "mc_val": _multicast_ptr(hv) if mc else 0, "mc_sel": _multicast_ptr(hs) if mc else 0})
+        self.multicast = bool(self.sets[0]["mc_val"])
         self.step = 0
 
     def next_set(self):
@@ -250,14 +288,23 @@ class ShardedMaxKAggregation:
         cuda_nccl = isinstance(self.compute, CudaCompute) and self.rows["indices"].is_cuda and \
             dist.get_backend(group) == "nccl" and self.world <= self.compute.k.MAX_PEERS and \
             self.compute.k._lib.maxk_banked_modulus(self.k) >= 4
+        multicast = os.environ.get("MAXK_NVLS", "1") == "1"
         if gather != "nccl" and cuda_nccl and os.environ.get("MAXK_PEER_GATHER", "1") == "1":
             try:
-                self.peer = PeerGather(self.world * self.m, self.k, self.rows["indices"].device, group)
+                self.peer = PeerGather(self.world * self.m, self.k, self.rows["indices"].device, group, multicast)
             except Exception as ex:          # no peer mapping on this system: NCCL all_gather does the same job
                 self.gather_error = repr(ex)[:300]
                 if gather == "peer":
                     raise
-        self.gather = "peer" if self.peer is not None else "nccl"
+        self.gather = ("peer+nvls" if self.peer.multicast else "peer") if self.peer is not None else "nccl"
+        # backward exchange: reduce_scatter inside the NVSwitch when the partial can live in multicast-mapped memory
+        self.peer_reduce = None
+        if self.peer is not None and multicast and backward_mode == "reduce_scatter" and (self.m * self.k) % 4 == 0:
+            try:
+                self.peer_reduce = PeerReduce(self.world * self.m, self.k, self.rows["indices"].device, group)
+            except Exception as ex:
+                self.gather_error = (self.gather_error or "") + " | backward: " + repr(ex)[:200]
+        self.reduce = "nvls" if self.peer_reduce is not None else ("nccl" if backward_mode == "reduce_scatter" else "none")
 
     def local_slab(self, full):
         """This rank's rows of a full [N, ...] tensor, zero-padded to the slab height m."""
@@ -275,7 +322,8 @@ class ShardedMaxKAggregation:
         if self.peer is not None and x_local.size(1) == 256:
             st = self.peer.next_set()
             masked = self.compute.k.topk_cbsr_to_peers(x_local, self.k, st["val_ptrs"], st["sel_ptrs"],
-                                                       row_offset=self.rank * self.m, want_masked=want_masked)
+                                                       row_offset=self.rank * self.m, want_masked=want_masked,
+                                                       mc_val_ptr=st["mc_val"], mc_sel_ptr=st["mc_sel"])
             st["hv"].barrier(channel=0)          # every rank's rows have landed in every rank's buffers
             return st["vals"], st["sel"], masked
         masked = None
@@ -297,6 +345,14 @@ class ShardedMaxKAggregation:
         if self.sel_full is None:
             raise RuntimeError("backward() before forward()")
         if self.backward_mode == "reduce_scatter":
+            if self.peer_reduce is not None and grad_local.is_cuda:
+                st = self.peer_reduce.next_set()
+                ip = self.rows["indptr"]
+                self.compute.k.sspmm_backward_csr(ip[:-1], ip[1:], self.rows["indices"], self.rows["values"], grad_local,
+                                                  self.sel_full, row_div=self.row_div, out=st["buf"])
+                st["h"].barrier(channel=0)               # every rank's partial is complete
+                gs = torch.empty(self.m, self.k, dtype=torch.float32, device=grad_local.device)
+                return self.compute.k.nvls_reduce(st["mc"] + self.rank * self.m * self.k * 4, gs)
             partial = self.compute.sspmm(self.rows, grad_local, self.sel_full, self.row_div)   # [P*m, k]
             return _reduce_scatter_sum(partial, self.group)
         grad = grad_local if self.row_div is None else grad_local / self.row_div.unsqueeze(-1)

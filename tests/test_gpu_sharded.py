@@ -61,7 +61,7 @@ def _run_rank(rank, world, port, mode, result_dir, partition="rows", gather="aut
         assert torch.equal(out2, out3) and torch.allclose(out2, out.detach(), rtol=1e-6, atol=1e-7)
         np.savez(os.path.join(result_dir, "rank%d.npz" % rank), out=out.detach().cpu().numpy(), gs=gs.cpu().numpy(),
                  xgrad=xl.grad.cpu().numpy(), lo=layer.rows["row_lo"], hi=layer.rows["row_hi"], edges=layer.rows["e_num"],
-                 gather=layer.gather)
+                 gather=layer.gather + " / " + layer.reduce)
     finally:
         dist.destroy_process_group()
 
