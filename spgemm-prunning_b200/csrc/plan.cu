@@ -7,10 +7,11 @@
 // neighbouring rows of a regular graph stay neighbours and share CSR sectors), cut into work items:
 //   * rows with >= 4096 edges: one row per warp, edges dealt to the 8 slots ("shared" items);
 //   * then groups of 8 rows of (nearly) equal degree, one per slot ("separate" items);
-//   * when the graph has no light rows to fill the last wave with (a regular high-degree graph), the last
-//     half wave of rows is again run one row per warp so that the grid drains evenly.
+//   * when the graph has no mass of light rows to fill the end of the kernel with (a regular high-degree graph),
+//     every warp gets the same whole number of groups and the rest of the rows is again run one row per warp, so
+//     that the grid drains evenly whatever the problem size.
 // Three small kernels (per-tile histogram, one-block scan, stable scatter), no host read-back: the plan can
-// be built inside a CUDA graph and is a pure function of (row_begin, row_end, tail_rows).
+// be built inside a CUDA graph and is a pure function of (row_begin, row_end, number of SMs).
 #include "slots.cuh"
 
 namespace maxk {
@@ -55,7 +56,7 @@ plan_hist_kernel(const int *__restrict__ row_begin, const int *__restrict__ row_
 
 // exclusive scan of hist (bucket-major) in place + plan header.  One block.
 __global__ void __launch_bounds__(1024)
-plan_scan_kernel(int *__restrict__ hist, int n_tiles, int n_rows, int tail_rows, int *__restrict__ header)
+plan_scan_kernel(int *__restrict__ hist, int n_tiles, int n_rows, int total_warps, int *__restrict__ header)
 {
     __shared__ int part[1024];
     const int total = kPlanBuckets * n_tiles;
@@ -83,9 +84,17 @@ plan_scan_kernel(int *__restrict__ hist, int n_tiles, int n_rows, int tail_rows,
         const int key_long = plan_key(kPlanLongDeg) + 1, key_tail = plan_key(kPlanTailDeg) + 1;
         const int n_long = hist[(size_t)key_long * n_tiles];
         const int p_tail = hist[(size_t)key_tail * n_tiles];       // rows with deg >= kPlanTailDeg
+        // A group of 8 rows is indivisible and costs a warp 8 row-times, a single shared row 1.  When the graph
+        // has no mass of light rows to even out the end of the kernel, every warp gets the same whole number of
+        // groups and the remaining rows (>= 3 per warp) are dealt as single rows by the dynamic scheduler -- on a
+        // small problem (one rank of an 8-GPU run: 12 rows per warp) a second group on a few warps would
+        // otherwise set the kernel time (measured 0.43 ms instead of 0.31 ms for 1/8 of the Reddit shape).
         int posC = n_rows, posD = n_rows;
-        if (n_rows - p_tail < tail_rows && p_tail > n_long) {      // too few light rows to even out the last wave
-            posC = max(n_long, p_tail - tail_rows);
+        if (n_rows - p_tail < 4 * total_warps && p_tail > n_long) {
+            const int heavy = p_tail - n_long;                         // rows of 128 .. 4095 edges
+            const int per_warp = heavy / total_warps;
+            const int groups_per_warp = per_warp >= 3 ? (per_warp - 3) / kSS : 0;
+            posC = n_long + min(groups_per_warp * total_warps, heavy / kSS) * kSS;
             posD = p_tail;
         }
         const int nA = n_long, nB = (posC - n_long + kSS - 1) / kSS, nC = posD - posC,
@@ -155,10 +164,10 @@ extern "C" size_t maxk_plan_workspace_bytes(int64_t n_rows)
     return sizeof(int) * kPlanBuckets * (n_tiles > 0 ? n_tiles : 1) + 16;
 }
 
-// half a wave of rows: what the last-wave rule of the plan compares the number of light rows with
-int plan_tail_rows()
+// warps of the forward's persistent grid: 2 CTAs x 8 warps per SM (spgemm_fwd.cu)
+int plan_total_warps()
 {
-    return device_sm_count() * 16 * kSS / 2;      // 2 CTAs x 8 warps per SM (spgemm_fwd.cu)
+    return device_sm_count() * 16;
 }
 
 extern "C" int maxk_plan_build(const int32_t *row_begin, const int32_t *row_end, int64_t n_rows, void *plan,
@@ -187,7 +196,7 @@ extern "C" int maxk_plan_build(const int32_t *row_begin, const int32_t *row_end,
         plan_hist_kernel<<<(n_tiles + kPlanWarps - 1) / kPlanWarps, kPlanThreads, 0, stream>>>(row_begin, row_end, (int)n_rows,
                                                                                                n_tiles, hist);
     }
-    plan_scan_kernel<<<1, 1024, 0, stream>>>(hist, tiles, (int)n_rows, plan_tail_rows(), header);
+    plan_scan_kernel<<<1, 1024, 0, stream>>>(hist, tiles, (int)n_rows, plan_total_warps(), header);
     if (n_tiles > 0)
         plan_scatter_kernel<<<(n_tiles + kPlanWarps - 1) / kPlanWarps, kPlanThreads, 0, stream>>>(
             row_begin, row_end, (int)n_rows, n_tiles, hist, p_row, p_beg, p_end);

@@ -41,7 +41,7 @@ constexpr int kPlanTicketSlots = 32;        // (next item, finished warps) pairs
 // + 1) in PLAN ORDER = rows sorted by degree bucket, longest first, stable inside a bucket.
 //   items [0, nA)            shared   : plan position i                       (deg >= kPlanLongDeg)
 //   items [nA, nA+nB)        separate : positions posB + 8 g .. (+8, clipped at posC)
-//   items [.., +nC)          shared   : positions posC + j                    (final wave of a regular graph)
+//   items [.., +nC)          shared   : positions posC + j                    (the evening-out rows of a regular graph)
 //   items [.., +nD)          separate : positions posD + 8 g .. (+8, clipped at n_rows)
 struct PlanView {
     int n_rows, nA, nB, nC, nD, posC, posD, n_items;
@@ -141,8 +141,7 @@ constexpr int kRing = 2 * kSW;              // ring entries per slot
 struct WindowMap {
     int base[kSS / 2];   // edge position fetched for window 0
     int wi0, wis;        // window entry written by fill instruction i: wi0 + i * wis (+ ring offset of the window)
-    int mult;            // edge positions per window (16 separate, 128 shared)
-    int ring;            // ring offset of odd windows (16 separate, 0 shared)
+    int shared;          // edge positions per window: 16 (separate) / 128 (shared); ring offset of odd windows: 16 / 0
     int lead;            // windows that must be parked ahead of the block being processed (1 aligned, else 0)
     int n_win;           // windows of the item
 };
@@ -156,8 +155,7 @@ __device__ __forceinline__ WindowMap make_window_map(const Desc &d, int shared, 
         for (int i = 0; i < kSS / 2; ++i) m.base[i] = b0 + 32 * i + lane;
         m.wi0 = lane;
         m.wis = 32;
-        m.mult = kSS * kSW;
-        m.ring = 0;
+        m.shared = 1;
         m.lead = 0;
         m.n_win = ((e0 - b0 + kSS - 1) / kSS + kSW - 1) / kSW;
     } else {
@@ -170,8 +168,7 @@ __device__ __forceinline__ WindowMap make_window_map(const Desc &d, int shared, 
         }
         m.wi0 = half * kCwStride + l16;
         m.wis = 2 * kCwStride;
-        m.mult = kSW;
-        m.ring = kSW;
+        m.shared = 0;
         m.lead = aligned;
         m.n_win = (steps + (kSW - 1) * (1 + aligned)) / kSW;
     }
@@ -201,7 +198,7 @@ __device__ __forceinline__ void fetch_window(const WindowMap &m, const int *__re
 {
 #pragma unroll
     for (int i = 0; i < kSS / 2; ++i) {
-        const int a = m.base[i] + w * m.mult;
+        const int a = m.base[i] + w * (m.shared ? kSS * kSW : kSW);
         pc[i] = 0;
         pw[i] = 0.f;
         if (a < n_edges) {
@@ -214,7 +211,7 @@ __device__ __forceinline__ void fetch_window(const WindowMap &m, const int *__re
 __device__ __forceinline__ void park_window(const WindowMap &m, int2 *cw, int w, const int (&pc)[kSS / 2],
                                             const float (&pw)[kSS / 2])
 {
-    const int off = m.wi0 + (w & 1) * m.ring;
+    const int off = m.wi0 + (m.shared ? 0 : (w & 1) * kSW);
 #pragma unroll
     for (int i = 0; i < kSS / 2; ++i) cw[off + i * m.wis] = make_int2(pc[i], __float_as_int(pw[i]));
 }

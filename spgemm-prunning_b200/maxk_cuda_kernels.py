@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libmaxk_b200.so")
+_LIB_PATH = os.environ.get("MAXK_B200_LIB") or os.path.join(_HERE, "lib", "libmaxk_b200.so")   # env: developer A/B builds
 
 FULL_DIM = 256          # cuda_kernel_bindings.cpp:70
 WARPS_PER_BLOCK = 12    # kernels/generate_meta.py:8 (metadata contract only)
