@@ -294,8 +294,15 @@ class ShardedMaxKAggregation:
                 self.peer = PeerGather(self.world * self.m, self.k, self.rows["indices"].device, group, multicast)
             except Exception as ex:          # no peer mapping on this system: NCCL all_gather does the same job
                 self.gather_error = repr(ex)[:300]
+            # every rank must take the same path (a rank alone at a barrier would hang the others)
+            if not self._all_ranks(self.peer is not None):
+                self.peer = None
                 if gather == "peer":
-                    raise
+                    raise RuntimeError("gather='peer' needs peer-mapped symmetric memory on every rank: %s" % self.gather_error)
+            elif not self._all_ranks(self.peer.multicast):
+                for st in self.peer.sets:
+                    st["mc_val"] = st["mc_sel"] = 0
+                self.peer.multicast = False
         self.gather = ("peer+nvls" if self.peer.multicast else "peer") if self.peer is not None else "nccl"
         # backward exchange: reduce_scatter inside the NVSwitch when the partial can live in multicast-mapped memory
         self.peer_reduce = None
@@ -304,7 +311,16 @@ class ShardedMaxKAggregation:
                 self.peer_reduce = PeerReduce(self.world * self.m, self.k, self.rows["indices"].device, group)
             except Exception as ex:
                 self.gather_error = (self.gather_error or "") + " | backward: " + repr(ex)[:200]
+            if not self._all_ranks(self.peer_reduce is not None):
+                self.peer_reduce = None
         self.reduce = "nvls" if self.peer_reduce is not None else ("nccl" if backward_mode == "reduce_scatter" else "none")
+
+    def _all_ranks(self, ok):
+        """True iff `ok` holds on every rank of the group."""
+        dev = self.rows["indices"].device
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
 
     def local_slab(self, full):
         """This rank's rows of a full [N, ...] tensor, zero-padded to the slab height m."""
