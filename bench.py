@@ -478,6 +478,28 @@ def run_ours(args, n, e):
                       "tolerance": "index sets bit-exact; |got-exp| <= 1e-6 + 1e-5|exp| (violation <= 1), max over ranks",
                       "ok": red[5] == 0.0}
             del x_g, g_g, vals_g, sel_g, pos
+        # the backward variant BASELINE.json names ("gradient rows exchanged with an NCCL allgather before local
+        # aggregation"), timed beside the default (reduce of the compact partial): same forward, same graph
+        ag_ms = None
+        if not args.no_allgather_variant and args.bwd_mode != "allgather":
+            layer_ag = ShardedMaxKAggregation(graph, k, backward_mode="allgather", partition=args.partition, gather=args.gather)
+            for _ in range(3):
+                layer_ag.forward(x)
+                layer_ag.backward(grad)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = _ev(), _ev()
+            a.record()
+            for _ in range(10):
+                layer_ag.forward(x)
+                layer_ag.backward(grad)
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / 10], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ag_ms = float(t.item())
+            del layer_ag
         del graph, out_l, gs_l
         torch.cuda.empty_cache()
 
@@ -513,6 +535,8 @@ def run_ours(args, n, e):
                              "process bound to the %d cores next to its GPU" % host_cores}
         if phases:
             parts["phases"] = phases
+        if ag_ms is not None:
+            parts["allgather_backward_variant_ms_per_step"] = ag_ms
         roof_bytes, roof_ms = None, None
         scaling = "strong"
 
@@ -580,6 +604,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check after the timed region")
     ap.add_argument("--no-sweep", action="store_true", help="skip the secondary configurations (extra.sweep)")
+    ap.add_argument("--no-allgather-variant", action="store_true",
+                    help="multi-GPU: do not also time the all_gather(gradient rows) backward variant")
     ap.add_argument("--phases", action="store_true", help="multi-GPU: add a per-phase split of the step to breakdown")
     ap.add_argument("--kind", default="uniform", choices=["uniform", "powerlaw"], help="degree distribution of the synthetic graph")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
