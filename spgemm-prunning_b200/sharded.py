@@ -305,8 +305,12 @@ class ShardedMaxKAggregation:
                 self.peer.multicast = False
         self.gather = ("peer+nvls" if self.peer.multicast else "peer") if self.peer is not None else "nccl"
         # backward exchange: reduce_scatter inside the NVSwitch when the partial can live in multicast-mapped memory
+        # (small partials only: the switch pulls every rank's WHOLE partial, own slab included, so above a few tens of
+        # MB it is link-bound at ~P/(P-1) times the bytes of a reduce_scatter -- products shape, 4 GPUs: 0.47 ms for a
+        # 313 MB partial -- while below it wins on latency: Reddit shape 48 us against 68 us)
         self.peer_reduce = None
-        if self.peer is not None and multicast and backward_mode == "reduce_scatter" and (self.m * self.k) % 4 == 0:
+        small = self.world * self.m * self.k * 4 <= int(os.environ.get("MAXK_NVLS_REDUCE_MAX_MB", "64")) << 20
+        if self.peer is not None and multicast and small and backward_mode == "reduce_scatter" and (self.m * self.k) % 4 == 0:
             try:
                 self.peer_reduce = PeerReduce(self.world * self.m, self.k, self.rows["indices"].device, group)
             except Exception as ex:
