@@ -202,8 +202,10 @@ def test_training_step_gradients_at_the_yelp_shape(layers):
     else:
         torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=1e-6)
         bad = ((out - ref).abs() > 1e-4 + 1e-3 * ref.abs()).float().mean().item()
-        assert bad < 0.01, "fraction of logits outside tolerance: %.4f" % bad
+        print("3 layers: fraction of logits outside tolerance %.5f" % bad)
+        assert bad < 0.02, "fraction of logits outside tolerance: %.4f" % bad
         for name, p in model.named_parameters():
             if p.grad is not None:
                 rel = float((grads[name] - p.grad).norm() / p.grad.norm().clamp(min=1e-30))
-                assert rel < 2e-2, "%s: relative gradient difference %.3e" % (name, rel)
+                print("   %s: relative gradient difference %.3e" % (name, rel))
+                assert rel < 1e-3, "%s: relative gradient difference %.3e" % (name, rel)
