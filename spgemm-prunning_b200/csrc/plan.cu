@@ -1,9 +1,9 @@
-// plan.cu -- the row plan of the slot-parallel SpGEMM / SSpMM kernels, built on the GPU (sm_100a).
+// plan.cu -- the row plan of the slot-parallel forward SpGEMM, built on the GPU (sm_100a).
 //
 // The reference partitions rows into <= 64-edge warp segments on the host (kernels/generate_meta.py:30-48)
-// and flushes every segment with 256 global atomics (kernels/spmm_maxk.cu:101-105).  Our kernels own whole
-// rows instead and process 8 of them in lockstep per warp (slots.cuh), so the partitioning metadata they
-// need is an ORDER: rows sorted by degree bucket, longest first (stable inside a bucket, so that
+// and flushes every segment with 256 global atomics (kernels/spmm_maxk.cu:101-105).  Our forward owns whole
+// rows instead and processes 8 of them in lockstep per warp (slots.cuh), so the partitioning metadata it
+// needs is an ORDER: rows sorted by degree bucket, longest first (stable inside a bucket, so that
 // neighbouring rows of a regular graph stay neighbours and share CSR sectors), cut into work items:
 //   * rows with >= 4096 edges: one row per warp, edges dealt to the 8 slots ("shared" items);
 //   * then groups of 8 rows of (nearly) equal degree, one per slot ("separate" items);

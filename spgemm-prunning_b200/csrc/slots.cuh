@@ -1,4 +1,5 @@
-// slots.cuh -- the slot-parallel execution scheme shared by the forward SpGEMM and the backward SSpMM.
+// slots.cuh -- the slot-parallel execution scheme of the forward SpGEMM (spgemm_fwd.cu).  (The backward SSpMM keeps
+// 8 lanes per edge: one vector reduction must cover a destination row's full 128-byte line, see sspmm_bwd.cu.)
 //
 // A warp is split into kSS = 8 edge SLOTS of kSL = 4 lanes.  A slot processes one edge per step; the
 // 4 lanes of a slot share the k entries of that edge's CBSR row (k/4 entries per lane).  Every slot has
