@@ -209,15 +209,21 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
                     if (8 * lane + i < dim) orow[8 * lane + i] = o[i];
             }
         } else {
-            // lane (q, t) reads 8 consecutive columns [32 n + 8 t, +8) of copy q = row of slot q
-            const int r = __shfl_sync(kFullMask, d_cur.r, q);
+            // lane l reads 8 consecutive columns [32 n + 8 te, +8) of copy qe = row of slot qe, with qe = l % 8 and
+            // te = l / 8: a 16-byte shared-memory access is served a quarter-warp (8 consecutive lanes) at a time
+            // and copy qe lives in banks [4 qe, 4 qe + 4), so the 8 lanes of a quarter must read 8 DIFFERENT copies
+            // (the accumulation's own mapping, 4 lanes per copy, made every access here a 4-way conflict:
+            // ncu 16 wavefronts per instruction instead of 4, 48 of the 137 shared-memory wavefronts per row
+            // of the Yelp shape)
+            const int qe = lane & (kSS - 1), te = lane >> 3;
+            const int r = __shfl_sync(kFullMask, d_cur.r, qe);
             float dv = 1.f;
             const bool has_div = row_div != nullptr && r >= 0;
             if (has_div) dv = __ldg(row_div + r);
             float *orow = out + (size_t)(r >= 0 ? r : 0) * ld_out;
 #pragma unroll
             for (int n = 0; n < kAccDim / 32; ++n) {
-                const int w0 = (8 * n + 2 * t) * 8 + q;                           // float4 index
+                const int w0 = (8 * n + 2 * te) * 8 + qe;                         // float4 index
                 const float4 x = acc4[w0], y = acc4[w0 + 8];
                 acc4[w0] = make_float4(0.f, 0.f, 0.f, 0.f);
                 acc4[w0 + 8] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,7 +233,7 @@ spgemm_fwd_slots_kernel(const int *__restrict__ plan, const int *__restrict__ id
                     for (int i = 0; i < 8; ++i) o[i] = div_guarded(o[i], dv);
                 }
                 if (r >= 0) {
-                    const int c0 = 32 * n + 8 * t;
+                    const int c0 = 32 * n + 8 * te;
                     if (vec_out) {
                         st_stream_f32x8(orow + c0, o);
                     } else {
