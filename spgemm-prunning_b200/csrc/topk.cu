@@ -85,8 +85,8 @@ __device__ __forceinline__ int count_ge(const uint32_t (&key)[8], uint32_t t, in
 // the largest key of the row.  Invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k.  Pivots come
 // from linear interpolation of the count (few steps on smooth data) with a plain bisection every fourth
 // step (guaranteed progress on anything); stops early when exactly k keys are at or above the pivot
-// (`exact`: no tie handling needed).  (p2, c2) is an optional second known point, count(>= p2) = c2
-// (pass p2 = 0 for none): it replaces whichever end of the bracket it tightens.
+// (`exact`: count(>= returned T) == k, no tie handling needed).  (p2, c2) is an optional second known point,
+// count(>= p2) = c2 (pass p2 = 0 for none): it replaces whichever end of the bracket it tightens.
 __device__ __forceinline__ uint32_t find_threshold(const uint32_t (&key)[8], int k, uint32_t kmin, uint32_t kmax,
                                                    bool &exact, int one, uint32_t p2 = 0u, int c2 = 0)
 {
@@ -99,25 +99,36 @@ __device__ __forceinline__ uint32_t find_threshold(const uint32_t (&key)[8], int
     if (p2 > lo && p2 < hi) {
         if (c2 >= k) { lo = p2; c_lo = c2; } else { hi = p2; c_hi = c2; }
     }
-    exact = (c_lo == k);
-    for (int it = 1; !exact && hi - lo > 1u; ++it) {
-        const uint32_t span = hi - lo;
+    // One count per step.  A pivot with exactly k keys at or above it collapses the bracket onto itself
+    // (lo = hi = pivot), so the span test alone ends the loop; every fourth step is a plain bisection, which
+    // bounds the search on anything (<= 4 * 32 steps) -- written as four copies of the step instead of a
+    // step counter (selects, not branches: straight-line code around one count; the ALU pipe is the bound).
+    uint32_t span = c_lo == k ? 0u : hi - lo;
+    auto step = [&](bool bisect) {
         // secant step: off = span * (c_lo - k + 1/2) / (c_lo - c_hi) in integers; counts are <= 256
-        // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32).  Every fourth step is a
-        // plain bisection, which bounds the search on anything (<= 4 * 32 steps); on the distributions
-        // simulated it costs the same number of steps as bisecting only when one end is stuck, with
-        // less bookkeeping.  Selects, not branches: the loop body is straight-line code around one count.
+        // (num < 2 * d, so num * floor(2^31 / d) < 2^32 is the fraction in Q32)
         const uint32_t num = (uint32_t)(2 * (c_lo - k) + 1);
-        const uint32_t sec = min(max(__umulhi(span, num * c_recip31[c_lo - c_hi]), 1u), span - 1u);
-        const uint32_t mid = lo + ((it & 3) == 0 ? (span >> 1) : sec);
+        const uint32_t sec = bisect ? 0u : min(max(__umulhi(span, num * c_recip31[c_lo - c_hi]), 1u), span - 1u);
+        const uint32_t mid = lo + (bisect ? (span >> 1) : sec);
         const int c = count_ge(key, mid, one);
-        const bool up = c >= k;                  // the lower end moves
+        const bool up = c >= k, dn = c <= k;     // both when c == k
         lo = up ? mid : lo;
         c_lo = up ? c : c_lo;
-        hi = up ? hi : mid;
-        c_hi = up ? c_hi : c;
-        exact = (c == k);
+        hi = dn ? mid : hi;
+        c_hi = dn ? c : c_hi;
+        span = hi - lo;
+    };
+    for (;;) {
+        if (span <= 1u) break;
+        step(false);
+        if (span <= 1u) break;
+        step(false);
+        if (span <= 1u) break;
+        step(false);
+        if (span <= 1u) break;
+        step(true);
     }
+    exact = c_lo == k;                           // count(>= lo) == k: no tie handling needed
     return lo;
 }
 
@@ -333,7 +344,10 @@ __device__ __forceinline__ void multimem_st_b32(void *mc, uint32_t bits)
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(__uint_as_float(bits)) : "memory");
 }
 
-template <int K>
+// PLAIN: values + uint8 selectors to local memory only (what the layer's forward pass launches): the optional
+// outputs (int32 / int64 indices, masked row, peer destinations) cost ~35 instructions per row in null checks
+// and predicated address arithmetic on the pipe that bounds the kernel, so they are compiled out.
+template <int K, bool PLAIN>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restrict__ out_val,
                    uint8_t *__restrict__ out_sel, int32_t *__restrict__ out_i32, int64_t *__restrict__ out_i64,
@@ -409,7 +423,7 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
             }
         }
 
-        if (masked != nullptr) {
+        if (!PLAIN && masked != nullptr) {
             float mv[8];
 #pragma unroll
             for (int s = 0; s < 8; ++s) mv[s] = selb[s] ? v[s] : 0.f;
@@ -426,13 +440,17 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
             int sz[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) sz[u] = __popc(bs[u]) + __popc(bs[u + 4]);
+            // base[u] = total size of the classes ranked before u; class a < b comes first iff sz[a] >= sz[b]
+            // (six warp-uniform compares)
+            const bool f01 = sz[0] >= sz[1], f02 = sz[0] >= sz[2], f03 = sz[0] >= sz[3];
+            const bool f12 = sz[1] >= sz[2], f13 = sz[1] >= sz[3], f23 = sz[2] >= sz[3];
+            const int base[4] = {(f01 ? 0 : sz[1]) + (f02 ? 0 : sz[2]) + (f03 ? 0 : sz[3]),
+                                 (f01 ? sz[0] : 0) + (f12 ? 0 : sz[2]) + (f13 ? 0 : sz[3]),
+                                 (f02 ? sz[0] : 0) + (f12 ? sz[1] : 0) + (f23 ? 0 : sz[3]),
+                                 (f03 ? sz[0] : 0) + (f13 ? sz[1] : 0) + (f23 ? sz[2] : 0)};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                int base = 0;
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    if (v != u && (sz[v] > sz[u] || (sz[v] == sz[u] && v < u))) base += sz[v];
-                const int p = base + __popc(bs[u] & lt) + __popc(bs[u + 4] & lt);
+                const int p = base[u] + __popc(bs[u] & lt) + __popc(bs[u + 4] & lt);
                 pos[u] = banked_mem_pos(p, K);
                 pos[u + 4] = banked_mem_pos(p + (selb[u] ? 1 : 0), K);
             }
@@ -455,22 +473,27 @@ topk_banked_kernel(const float *__restrict__ x, int64_t n_rows, float *__restric
                 const uint2 ent = *reinterpret_cast<const uint2 *>(ent_w + 2 * i);
                 const int c = (int)ent.y;
                 const int64_t o = r * K + i;
-                if (peers.n == 0) {
+                if (PLAIN) {
                     out_val[o] = __uint_as_float(ent.x);
-                    if (out_sel) out_sel[o] = (uint8_t)c;
-                } else if (peers.mc_val != nullptr) {
-                    multimem_st_b32(peers.mc_val + o, ent.x);       // the switch replicates the store to every rank
+                    out_sel[o] = (uint8_t)c;
                 } else {
-                    for (int p = 0; p < peers.n; ++p) {
-                        peers.val[p][o] = __uint_as_float(ent.x);
-                        peers.sel[p][o] = (uint8_t)c;
+                    if (peers.n == 0) {
+                        out_val[o] = __uint_as_float(ent.x);
+                        if (out_sel) out_sel[o] = (uint8_t)c;
+                    } else if (peers.mc_val != nullptr) {
+                        multimem_st_b32(peers.mc_val + o, ent.x);   // the switch replicates the store to every rank
+                    } else {
+                        for (int p = 0; p < peers.n; ++p) {
+                            peers.val[p][o] = __uint_as_float(ent.x);
+                            peers.sel[p][o] = (uint8_t)c;
+                        }
                     }
+                    if (out_i32) out_i32[o] = c;
+                    if (out_i64) out_i64[o] = c;
                 }
-                if (out_i32) out_i32[o] = c;
-                if (out_i64) out_i64[o] = c;
             }
         }
-        if (peers.n != 0 && peers.mc_val != nullptr && lane < K / 4) {   // selectors: 4 per 32-bit multicast store
+        if (!PLAIN && peers.n != 0 && peers.mc_val != nullptr && lane < K / 4) {   // selectors: 4 per 32-bit multicast store
             uint32_t w = 0u;
 #pragma unroll
             for (int b = 0; b < 4; ++b) w |= (ent_w[2 * (4 * lane + b) + 1] & 0xffu) << (8 * b);
@@ -597,7 +620,7 @@ dense_spmm_kernel(const int *__restrict__ indptr, const int *__restrict__ idx, c
 
 // One resident wave: the grid is what the device holds at once (cached per device), rows beyond it are
 // taken by the grid-stride loop, so that no SM idles while a partial second wave drains.
-template <int K>
+template <int K, bool PLAIN>
 static cudaError_t launch_topk_banked(const float *x, int64_t n_rows, float *cbsr_val, uint8_t *cbsr_sel,
                                       int32_t *idx_i32, int64_t *idx_i64, float *masked, cudaStream_t st,
                                       const PeerOut &peers)
@@ -610,13 +633,13 @@ static cudaError_t launch_topk_banked(const float *x, int64_t n_rows, float *cbs
     int &cap = (dev >= 0 && dev < kMaxCachedDevices) ? resident[dev] : local;
     if (cap == 0) {
         int per_sm = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_banked_kernel<K>, kTopkThreads, 0);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_banked_kernel<K, PLAIN>, kTopkThreads, 0);
         if (err != cudaSuccess) return err;
         cap = device_sm_count() * (per_sm < 1 ? 1 : per_sm);
     }
     const int64_t need = (n_rows + kTopkWarps - 1) / kTopkWarps;
     const int grid = (int)(need < cap ? need : cap);
-    topk_banked_kernel<K><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1, peers);
+    topk_banked_kernel<K, PLAIN><<<grid, kTopkThreads, 0, st>>>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, 1, peers);
     return cudaGetLastError();
 }
 
@@ -624,14 +647,22 @@ static cudaError_t dispatch_topk_banked(int k, const float *x, int64_t n_rows, f
                                         int32_t *idx_i32, int64_t *idx_i64, float *masked, cudaStream_t st,
                                         const PeerOut &peers)
 {
+    const bool plain = idx_i32 == nullptr && idx_i64 == nullptr && masked == nullptr && peers.n == 0 && cbsr_sel != nullptr;
+#define MAXK_TOPK_CASE(KK)                                                                                              \
+    case KK:                                                                                                            \
+        return plain ? launch_topk_banked<KK, true>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers) \
+                     : launch_topk_banked<KK, false>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
     switch (k) {
-        case 8: return launch_topk_banked<8>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
-        case 16: return launch_topk_banked<16>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
-        case 32: return launch_topk_banked<32>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
-        case 64: return launch_topk_banked<64>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
-        case 96: return launch_topk_banked<96>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
-        default: return launch_topk_banked<128>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+        MAXK_TOPK_CASE(8)
+        MAXK_TOPK_CASE(16)
+        MAXK_TOPK_CASE(32)
+        MAXK_TOPK_CASE(64)
+        MAXK_TOPK_CASE(96)
+        default: break;
     }
+    return plain ? launch_topk_banked<128, true>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers)
+                 : launch_topk_banked<128, false>(x, n_rows, cbsr_val, cbsr_sel, idx_i32, idx_i64, masked, st, peers);
+#undef MAXK_TOPK_CASE
 }
 
 static int grid_for_rows(int64_t n_rows)

@@ -39,23 +39,23 @@ def find_threshold(key, k, p2=0, c2=0):
         else:
             hi, c_hi = p2, c2
     assert c_lo >= k > c_hi
-    exact = c_lo == k
+    span = 0 if c_lo == k else hi - lo
     it = 1
-    while not exact and hi - lo > 1:
-        span = hi - lo
+    while span > 1:
         num = 2 * (c_lo - k) + 1
         frac = (num * ((1 << 31) // (c_lo - c_hi))) & 0xffffffff
         assert num * ((1 << 31) // (c_lo - c_hi)) < (1 << 32)            # the Q32 fraction never overflows
         sec = min(max((span * frac) >> 32, 1), span - 1)
-        mid = lo + ((span >> 1) if (it & 3) == 0 else sec)
+        mid = lo + ((span >> 1) if (it & 3) == 0 else sec)              # the kernel unrolls the step four times
         assert lo < mid < hi
         c = count(mid)
         if c >= k:
             lo, c_lo = mid, c
-        else:
+        if c <= k:                                                       # c == k collapses the bracket: lo = hi = mid
             hi, c_hi = mid, c
-        exact = c == k
+        span = hi - lo
         it += 1
+    exact = c_lo == k
     return lo, exact, steps
 
 
