@@ -17,7 +17,7 @@
 //      popcounts: column order (MAXK_ORDER_COLUMN_ASC), bank-residue-major order (MAXK_ORDER_BANKED,
 //      what the SpGEMM/SSpMM kernels are conflict-minimal on), or rank-sorted by (value desc, column
 //      asc) through shared memory (MAXK_ORDER_VALUE_DESC).
-// Two kernels: topk_banked_kernel<K> for the layer's hot configuration (dim 256, banked order,
+// Two kernels: topk_banked_kernel<K, PLAIN> for the layer's hot configuration (dim 256, banked order,
 // k in {8, 16, 32, 64}; see its header below) and the general topk_cbsr_kernel for everything else.
 // The same pass can write the dense masked row (the MaxK nonlinearity output), so the
 // reference's topk + zeros_like + scatter_ + multiply (4 dense passes) is one read + one write.
@@ -321,8 +321,8 @@ topk_cbsr_kernel(const float *__restrict__ x, int64_t n_rows, int dim, int k, in
 // ---------------------------------------------------------------------------------------------
 // The layer's hot configuration: dim == 256, MAXK_ORDER_BANKED, k in {8, 16, 32, 64}.
 //
-// Same selection as the general kernel above, arranged for the fewest issued instructions (the general
-// kernel issues ~565 warp instructions per row and is issue-bound at 78 % of the issue slots, 19 % of
+// Same selection as the general kernel above, arranged for the fewest issued instructions (386 warp
+// instructions per row for k = 32, ALU pipe 75 % busy; the general kernel issues ~565 and reaches 19 % of the
 // HBM bandwidth): lane l owns the 8 CONSECUTIVE columns 8l .. 8l+7 (one 32-byte load per lane), so
 // that a column's bank-residue class mod 8 is its register slot and the banked output position of an
 // entry is a prefix over the slots' ballots instead of a lane-group exchange; (value, column) pairs are
