@@ -1,5 +1,5 @@
 """Developer tool (GPU): time the forward / backward on BASELINE shapes (median of 8, CUDA events).
-    python tools/fwd_once.py [--shapes reddit,yelp,...] [--k 32]"""
+    python tools/fwd_once.py [--shapes reddit,yelp,...] [--k 32 | --k 8,64]"""
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "spgemm-prunning_b200")):
@@ -19,12 +19,12 @@ def med(fn, warm=3, reps=8):
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--shapes", default="reddit,yelp,flickr,proteins,products,reddit_pl")
-ap.add_argument("--k", type=int, default=0)
+ap.add_argument("--k", default="0", help="k, or a comma list of k (all run on every shape)")
 args = ap.parse_args()
-for shape in args.shapes.split(","):
+for shape, k_arg in ((s_, int(k_)) for s_ in args.shapes.split(",") for k_ in args.k.split(",")):
     name, kind = (shape[:-3], "powerlaw") if shape.endswith("_pl") else (shape, "uniform")
     n, e = SHAPES[name]
-    k = args.k or (64 if name == "proteins" else 32)
+    k = k_arg or (64 if name == "proteins" else 32)
     g = synth_graph(n, e, seed=123, kind=kind, device="cuda")
     ip, ix, va = g["indptr"], g["indices"], g["values"]
     x = torch.rand(n, 256, device="cuda"); grad = torch.rand(n, 256, device="cuda")
