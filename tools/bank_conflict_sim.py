@@ -36,7 +36,26 @@ def by_size(row, m):
     return np.array([c for l in cls for c in l])
 
 
+def epilogue_wavefronts(lane_map):
+    """Wavefronts of one 16-byte access of the per-row epilogue: a quarter-warp (8 consecutive lanes) is served
+    per pass, a pass costs its worst bank multiplicity.  lane_map(lane) -> (copy q, word row j): the float4 at
+    words 32 j + 4 q .. + 3, i.e. banks [4 q, 4 q + 4)."""
+    total = 0
+    for quarter in range(4):
+        hits = {}
+        for lane in range(8 * quarter, 8 * quarter + 8):
+            q, j = lane_map(lane)
+            for b in range(4 * q, 4 * q + 4):
+                hits.setdefault(b, set()).add(32 * j + b)
+        total += max(len(v) for v in hits.values())
+    return total
+
+
 def main():
+    # the epilogue's two lane maps (csrc/spgemm_fwd.cu): the accumulation's own (4 lanes per copy) against lane l on
+    # copy l % 8 -- ncu measured 16 and 4 wavefronts per LDS.128 / STS.128 (profiles/r02_ncu_full_fwd_yelp_k32_epilogue_fix.txt)
+    print("epilogue, wavefronts per 16-byte access: lanes (q, t) = (l / 4, l %% 4): %d   lanes (q, t) = (l %% 8, l / 8): %d"
+          % (epilogue_wavefronts(lambda l: (l // 4, 2 * (l % 4))), epilogue_wavefronts(lambda l: (l % 8, 2 * (l // 8)))))
     rng = np.random.default_rng(0)
     print("%4s %22s %8s %8s %8s %8s" % ("k", "layout", "floor", "random", "plain", "by size"))
     for k in (8, 16, 32, 64, 128):
