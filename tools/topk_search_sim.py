@@ -11,6 +11,9 @@ rules:
               is expected (distribution-free: the top-k of a row hit 32 (1 - (31/32)^k) distinct lanes), then
               the secant rule inside that bracket.  Needs a 32-key warp sort (~50 instructions, about one
               count step) that the numbers below do not include.
+  est         the secant rule without the first count: the count at the lower end of the bracket is a rank statistic
+              (distribution-free for iid rows), so a constant stands in for it
+  warm        est + the previous row's threshold as the first pivot (helps when consecutive rows have similar scale)
 """
 import numpy as np
 
@@ -98,20 +101,65 @@ def rule_lane_rank(key, k, slope=1.5):
     return secant(key, k, lo, hi, c_lo, c_hi, n)
 
 
+def secant_t(key, k, lo, hi, c_lo, c_hi, n):
+    """secant() that also returns the threshold found (and tolerates an estimated c_lo)."""
+    it = 0
+    while hi - lo > 1:
+        span = hi - lo
+        it += 1
+        d = max(c_lo - c_hi, 1)
+        sec = min(max((span * (((2 * (c_lo - k) + 1) * recip31(d)) & 0xffffffff)) >> 32, 1), span - 1)
+        mid = lo + ((span >> 1) if it % 4 == 0 else sec)
+        c = int((key >= mid).sum())
+        n += 1
+        if c == k:
+            return n, mid
+        if c > k:
+            lo, c_lo = mid, c
+        else:
+            hi, c_hi = mid, c
+    return n, lo
+
+
+EST = {8: 96, 16: 97, 32: 99, 64: 138}     # median count at the lower end of the bracket, iid rows of 256
+
+
+def rule_warm(key, k, t_prev=None):
+    m1, m2 = lane_stats(key)
+    lo, hi = (int(m1.min()) if k <= 32 else int(m2.min())), int(m1.max()) + 1
+    c_lo, c_hi, n = max(EST[k], k + 1), 0, 0
+    if t_prev is not None and lo < t_prev < hi:
+        c = int((key >= t_prev).sum())
+        n = 1
+        if c == k:
+            return n, t_prev
+        if c > k:
+            lo, c_lo = t_prev, c
+        else:
+            hi, c_hi = t_prev, c
+    return secant_t(key, k, lo, hi, c_lo, c_hi, n)
+
+
 def main():
     rng = np.random.default_rng(0)
     dists = (("U[0,1)", lambda: rng.random(256, dtype=np.float32)),
              ("N(0,1)", lambda: rng.standard_normal(256).astype(np.float32)),
              ("relu(N(0,1))", lambda: np.maximum(rng.standard_normal(256), 0).astype(np.float32)),
-             ("lognormal(0,2)", lambda: np.exp(2 * rng.standard_normal(256)).astype(np.float32)))
-    print("%-16s %4s %8s %8s %10s" % ("distribution", "k", "secant", "+m2", "lane-rank"))
+             ("lognormal(0,2)", lambda: np.exp(2 * rng.standard_normal(256)).astype(np.float32)),
+             ("N(0,1) x row scale", lambda: (np.exp(1.5 * rng.standard_normal()) * rng.standard_normal(256)).astype(np.float32)))
+    print("%-18s %4s %8s %8s %10s %8s %8s" % ("distribution", "k", "secant", "+m2", "lane-rank", "est", "warm"))
     for name, gen in dists:
         for k in (8, 16, 32, 64):
             rows = [keys_of(gen()) for _ in range(300)]
             a = np.mean([rule_secant(r, k) for r in rows])
             b = np.mean([rule_secant(r, k, True) for r in rows])
             c = np.mean([rule_lane_rank(r, k) for r in rows])
-            print("%-16s %4d %8.2f %8.2f %10.2f" % (name, k, a, b, c))
+            e = np.mean([rule_warm(r, k)[0] for r in rows])
+            w, t_prev = [], None
+            for r in rows:
+                n, t_prev = rule_warm(r, k, t_prev)
+                w.append(n)
+            print("%-18s %4d %8.2f %8.2f %10.2f %8.2f %8.2f" % (name, k, a, b, c, e, np.mean(w)))
 
 
 if __name__ == "__main__":
